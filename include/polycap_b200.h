@@ -1,0 +1,88 @@
+/*
+ * include/polycap_b200.h -- additive, GPU-specific entry points of libpolycap_b200.so.
+ *
+ * Everything in include/polycap.h keeps the reference's semantics.  The functions here expose
+ * what the reference API cannot express: batched replay of many photons in one kernel launch,
+ * runs addressed by photon id (Philox4x32-10 stream per id, so any GPU can take any id range),
+ * tally-only runs beyond what `int n_photons` x n_energies can materialise, and device-resident
+ * tallies that a caller (e.g. torch.distributed / NCCL) can all-reduce without a host round trip.
+ *
+ * C ABI only: plain pointers and sizes, no CUDA or torch types in any signature
+ * (streams and device pointers travel as void* / double* / int64_t*).
+ */
+#ifndef POLYCAP_B200_H
+#define POLYCAP_B200_H
+
+#include "polycap.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* layout of the int64 counter block (host or device), one all-reduce covers it */
+enum {
+	POLYCAP_B200_C_IDS = 0,         /* photon ids consumed (every call of the sampler) */
+	POLYCAP_B200_C_EXIT,            /* photons that reached the exit window (reference: iexit) */
+	POLYCAP_B200_C_NOT_ENTERED,     /* hit the glass at the entrance (reference: not_entered) */
+	POLYCAP_B200_C_NOT_TRANSMITTED, /* absorbed inside (reference: not_transmitted) */
+	POLYCAP_B200_C_UNCOUNTED,       /* -2, -1, or returned 1 outside the exit window: in no reference counter */
+	POLYCAP_B200_C_REFL_EXIT,       /* sum of i_refl over exit photons (what the reference prints) */
+	POLYCAP_B200_C_REFL_ALL,        /* reflection events of all photons */
+	POLYCAP_B200_C_SEG_STEPS,       /* capillary segments visited */
+	POLYCAP_B200_C_SOLVES,          /* full ray/cone solves */
+	POLYCAP_B200_C_LAUNCHED,
+	POLYCAP_B200_N_COUNTERS = 16
+};
+
+/* number of usable CUDA devices (0 when there is no driver/device) and the last device-side error text */
+POLYCAP_EXTERN int polycap_b200_device_count(void);
+POLYCAP_EXTERN const char *polycap_b200_last_error(void);
+POLYCAP_EXTERN const char *polycap_b200_optconst_provider(void);
+
+/* amu[i] (1/cm) and scatf[i] exactly as the library derives them for `description`
+ * (replaces the per-photon polycap_photon_scatf of src/polycap-photon.c:22-94). */
+POLYCAP_EXTERN bool polycap_b200_optical_constants(polycap_description *description, size_t n_energies, const double *energies, double *amu,
+						   double *scatf, polycap_error **error);
+
+/* Batched polycap_photon_launch (src/polycap-photon.c:390-955): n photons, one launch.
+ * Inputs  start_coords/start_direction/start_electric_vector: [n][3].
+ * amu/scatf may be NULL (then the provider above is used) or [n_energies] arrays to pin them.
+ * Outputs ret[n] (1/0/2/-2/-1), exit_coords/exit_direction/exit_electric_vector [n][3] (the state
+ * the reference leaves in the photon struct: last wall hit, not the exit plane), i_refl[n],
+ * d_travel[n], weights [n][n_energies].  Any output pointer may be NULL. */
+POLYCAP_EXTERN bool polycap_b200_photon_launch_batch(polycap_description *description, size_t n_energies, const double *energies,
+						     const double *amu, const double *scatf, int64_t n, const double *start_coords,
+						     const double *start_direction, const double *start_electric_vector, bool leak_calc, int *ret,
+						     double *exit_coords, double *exit_direction, double *exit_electric_vector, int64_t *i_refl,
+						     double *d_travel, double *weights, int64_t *counters, polycap_error **error);
+
+/* Source-driven run over photon ids [id0, id0+n_ids) with seed `seed`, results on the host:
+ * sum_weights[nE] (exit photons only), counters[POLYCAP_B200_N_COUNTERS], optional status[n_ids]
+ * (1 exit, 0 absorbed, 2 not entered, -2/-1, 3 = reached the end outside the exit window) and optional
+ * rec[n_ids][17+nE]: for exit photons the 17 values of struct _polycap_images (src start x,y; start x,y;
+ * start dir x,y; start elecv x,y; exit x,y,z; exit dir x,y; exit elecv x,y; n_refl; d_travel) + weights. */
+POLYCAP_EXTERN bool polycap_b200_source_run_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, bool leak_calc,
+						double *sum_weights, int64_t *counters, int8_t *status, double *rec, polycap_error **error);
+
+/* ---- sessions: device-resident tallies for benchmarks and multi-GPU reductions -------------- */
+typedef struct _polycap_b200_session polycap_b200_session;
+
+/* binds `source` to CUDA device `device` (-1: current / env POLYCAP_B200_DEVICE) and uploads its tables */
+POLYCAP_EXTERN polycap_b200_session *polycap_b200_session_new(polycap_source *source, int device, uint64_t seed, polycap_error **error);
+POLYCAP_EXTERN void polycap_b200_session_free(polycap_b200_session *session);
+/* Enqueues, on `cuda_stream` (a cudaStream_t cast to void*, NULL = default stream), the trace of ids
+ * [id0, id0+n_ids) in waves of at most wave_size ids and ACCUMULATES into the caller's DEVICE buffers
+ * d_sum_weights[nE] (double) and d_counters[POLYCAP_B200_N_COUNTERS] (int64).  Asynchronous: returns
+ * after the launches are queued.  Tally-only: no per-photon records are kept. */
+POLYCAP_EXTERN bool polycap_b200_session_run(polycap_b200_session *session, int64_t id0, int64_t n_ids, int64_t wave_size, void *cuda_stream,
+					     double *d_sum_weights, int64_t *d_counters, polycap_error **error);
+/* phase-vote thresholds (lanes) and resident CTAs per SM of the tracer; negative keeps the current value */
+POLYCAP_EXTERN void polycap_b200_session_tune(polycap_b200_session *session, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm);
+
+/* FP64 FMA throughput of `device` in TFLOP/s (2 flops per DFMA) -- the roofline denominator */
+POLYCAP_EXTERN double polycap_b200_dfma_peak_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+/*
+ * pcb_gpu.h -- host-side handle on the device-resident optic and the kernel launchers.
+ * Internal to libpolycap_b200 (the C ABI is include/polycap.h + include/polycap_b200.h).
+ */
+#ifndef PCB_GPU_H
+#define PCB_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcb_gpu_optic pcb_gpu_optic;
+
+typedef struct {
+	int nmax;
+	const double *z, *cap, *ext; /* nmax+1 each */
+	double sig_rough;
+	int64_t n_cap;
+	double density;
+	size_t n_energies;
+	const double *energies, *amu, *scatf;
+} pcb_optic_desc;
+
+typedef struct {
+	double d_source, src_x, src_y, src_sigx, src_sigy, src_shiftx, src_shifty, hor_pol;
+} pcb_source_desc;
+
+/* accumulated over ids, all int64 so one NCCL all-reduce covers them */
+enum {
+	PCB_C_IDS = 0,          /* photon ids consumed */
+	PCB_C_EXIT,             /* reached the exit window */
+	PCB_C_NOT_ENTERED,      /* hit the glass at the entrance (launch code 2) */
+	PCB_C_NOT_TRANSMITTED,  /* absorbed (launch code 0) */
+	PCB_C_UNCOUNTED,        /* -2, -1 and "returned 1 but missed the exit window" */
+	PCB_C_REFL_EXIT,        /* sum of i_refl over exit photons (what the reference prints) */
+	PCB_C_REFL_ALL,         /* capil_reflect events of all photons */
+	PCB_C_SEG_STEPS,        /* segments visited */
+	PCB_C_SOLVES,           /* full quadratic solves */
+	PCB_C_LAUNCHED,
+	PCB_C_COUNT = 16
+};
+
+const char *pcb_gpu_last_error(void);
+int pcb_gpu_device_count(void);
+
+/* Uploads profile tables and per-energy optical constants to `device` (-1: current default). */
+pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc *d);
+void pcb_gpu_optic_destroy(pcb_gpu_optic *g);
+int pcb_gpu_optic_device(const pcb_gpu_optic *g);
+int pcb_gpu_optic_n_energies(const pcb_gpu_optic *g);
+
+/* Tuning knobs (phase-vote thresholds in lanes, CTAs per SM, exact-check mode); <0 keeps the default. */
+void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm, int all_slow);
+
+/* Replay: n start states in host memory -> per-photon results in host memory.
+ * out_state: [n][11] = exit coords(3), exit dir(3), exit elecv(3), d_travel, capil_trace calls */
+int pcb_gpu_replay(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state,
+		   int64_t *irefl, double *weights, int64_t *counters /* [PCB_C_COUNT] or NULL */);
+
+/* One source-driven wave over ids [id0, id0+n_ids) on `stream` (a cudaStream_t, NULL = default).
+ * Device-resident accumulation: d_sum_weights[nE] += exit weights, d_counters[PCB_C_COUNT] += ...
+ * n_wanted > 0 cuts the wave after its n_wanted-th exit photon (ids beyond the cut are not consumed).
+ * If rec_fields/rec_weights (device, capacity rec_cap records) are given, exit records are appended in
+ * id order at rec_base.  Returns the number of ids consumed via *ids_used and exits via *n_exit
+ * (this synchronises the stream when either pointer or n_wanted is given). */
+int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
+		     double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap, int64_t rec_base,
+		     void *stream, int64_t *ids_used, int64_t *n_exit);
+
+/* dense per-id view of the last wave (debug / parity): status[n] and the 17+nE record of every id */
+int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, double *rec /* [n][17+nE] or NULL */);
+
+/* device memory helpers for callers that do not link the CUDA runtime */
+void *pcb_gpu_malloc(int device, size_t bytes);
+void pcb_gpu_free(int device, void *p);
+int pcb_gpu_memset(int device, void *p, int v, size_t bytes, void *stream);
+int pcb_gpu_copy_to_host(int device, void *dst, const void *src_dev, size_t bytes, void *stream);
+int pcb_gpu_sync(int device, void *stream);
+
+/* FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), timed with CUDA events */
+double pcb_gpu_dfma_peak(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

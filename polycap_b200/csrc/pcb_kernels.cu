@@ -1,0 +1,726 @@
+/*
+ * pcb_kernels.cu -- kernel launchers of libpolycap_b200 (sm_100a).
+ *
+ *   pcb_trace_kernel     persistent warp-synchronous tracer            (pcb_trace.cuh)
+ *   wave_scan_*          exclusive scan of the per-id exit flags: exit photons get their
+ *                        record slot in id order (deterministic output, reference: slot j of
+ *                        source.c:745)
+ *   wave_tally_*         fixed-order reduction of exit weights and counters for ids below
+ *                        the cut (source.c:893-896, 963-980)
+ *   wave_compact_*       dense per-id records -> packed struct _polycap_images arrays
+ *   dfma_peak_kernel     FP64 FMA throughput microbenchmark (roofline denominator)
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pcb_gpu.h"
+#include "pcb_trace.cuh"
+
+extern "C" void pcb_energy_constants(size_t n_energies, const double *energies, const double *amu, const double *scatf, double density, double *out);
+
+#define COSPI_6_HOST 0.86602540378443864676
+
+static thread_local std::string g_last_error;
+
+#define CK(call)                                                                                              \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                      \
+		if (e_ != cudaSuccess) {                                                                      \
+			char b_[512];                                                                         \
+			snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+			g_last_error = b_;                                                                    \
+			return -1;                                                                            \
+		}                                                                                             \
+	} while (0)
+
+extern "C" const char *pcb_gpu_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int pcb_gpu_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		g_last_error = "cudaGetDeviceCount failed: no usable CUDA device/driver";
+		return 0;
+	}
+	return n;
+}
+
+/* ------------------------------------------------------------------ device optic */
+
+struct pcb_gpu_optic {
+	int device = 0;
+	int sm_count = 0;
+	int nmax = 0, nE = 0;
+	PcbOptic o{};
+	double *d_tables = nullptr; /* z, cap, ext, hexz, rm: 5 x tb bytes */
+	double *d_ec = nullptr;
+	double *d_wscratch = nullptr;
+	PcbWorkCounters *d_wc = nullptr;
+	size_t table_bytes = 0; /* tb */
+	int threads = 256, ctas_per_sm = 2;
+	int thr_cand = 12, thr_refl = 12, thr_new = 8;
+	int tables_in_smem = 1;
+	double cap0 = 0, ext0 = 0;
+	/* wave buffers (grown on demand) */
+	int64_t wave_cap = 0;
+	int8_t *d_status = nullptr;
+	double *d_fields = nullptr;
+	int *d_irefl = nullptr;
+	double *d_weights = nullptr;
+	int64_t *d_rank = nullptr;
+	int64_t *d_blocksum = nullptr;
+	int64_t *d_cutinfo = nullptr; /* [0] cut, [1] exits below cut, [2] total exits */
+	double *d_partial = nullptr;
+	int64_t *d_cpartial = nullptr;
+	int64_t last_wave_n = 0;
+	/* replay buffers */
+	int64_t replay_cap = 0;
+	double *d_rin = nullptr;
+};
+
+static int pick_device(int device)
+{
+	if (device >= 0)
+		return device;
+	const char *env = getenv("POLYCAP_B200_DEVICE");
+	if (env && *env)
+		return atoi(env);
+	int cur = 0;
+	if (cudaGetDevice(&cur) != cudaSuccess)
+		return 0;
+	return cur;
+}
+
+extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc *d)
+{
+	int ndev = pcb_gpu_device_count();
+	if (ndev <= 0)
+		return nullptr;
+	device = pick_device(device);
+	if (device >= ndev) {
+		g_last_error = "requested CUDA device does not exist";
+		return nullptr;
+	}
+	if (cudaSetDevice(device) != cudaSuccess) {
+		g_last_error = "cudaSetDevice failed";
+		return nullptr;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+		g_last_error = "cudaGetDeviceProperties failed";
+		return nullptr;
+	}
+	if (prop.major < 9) {
+		g_last_error = "polycap-b200 needs an sm_100a (Blackwell) device";
+		return nullptr;
+	}
+	pcb_gpu_optic *g = new pcb_gpu_optic();
+	g->device = device;
+	g->sm_count = prop.multiProcessorCount;
+	g->nmax = d->nmax;
+	g->nE = (int)d->n_energies;
+	const int n = d->nmax + 1;
+	const size_t tb = ((size_t)(n + 1) * 8 + 15) & ~(size_t)15; /* one padded entry: the reference can read index nmax+1 */
+	g->table_bytes = tb;
+	const size_t tn = tb / 8;
+
+	double n_shells = round(sqrt(12. * d->n_cap - 3.) / 6. - 0.5);
+	std::vector<double> h(5 * tn, 0.0);
+	double *hz = h.data(), *hcap = hz + tn, *hext = hcap + tn, *hhex = hext + tn, *hrm = hhex + tn;
+	const double eps = 1e-9;
+	double m_safe = 1e300;
+	bool mono_ok = true;
+	for (int i = 0; i < n; i++) {
+		hz[i] = d->z[i];
+		hcap[i] = d->cap[i];
+		hext[i] = d->ext[i];
+		hhex[i] = d->ext[i] / (2. * COSPI_6_HOST * (n_shells + 1));
+		hrm[i] = d->cap[i] * d->cap[i] * (1.0 - eps);
+		double apo = sqrt((d->ext[i] * d->ext[i]) - ((d->ext[i] / 2.) * (d->ext[i] / 2.)));
+		double room = (apo * (1.0 - eps) - d->cap[i]) / hhex[i];
+		if (!(room < 1e300))
+			room = -1;
+		if (room < m_safe)
+			m_safe = room;
+		if (!(d->cap[i] < apo * (1.0 - eps) && d->cap[i] < d->ext[i] * (1.0 - eps) && d->cap[i] * d->cap[i] < d->ext[i] * (1.0 - eps)))
+			mono_ok = false;
+		if (!(d->cap[i] > 0) || !(d->ext[i] > 0))
+			m_safe = -1;
+	}
+	for (size_t i = n; i < tn; i++) {
+		hz[i] = hz[n - 1]; hcap[i] = hcap[n - 1]; hext[i] = hext[n - 1]; hhex[i] = hhex[n - 1]; hrm[i] = 0.0;
+	}
+	for (int i = 0; i + 1 < n; i++)
+		if (!(d->z[i + 1] > d->z[i]))
+			m_safe = -1; /* non-monotonic z: only the exact path is trusted */
+
+	PcbOptic &o = g->o;
+	o.nmax = d->nmax;
+	o.tstride = (int)tn;
+	o.n_energies = g->nE;
+	o.mono = (n_shells == 0.);
+	o.all_slow = getenv("POLYCAP_B200_EXACT_CHECKS") ? 1 : 0;
+	o.n_shells = n_shells;
+	o.sig_rough = d->sig_rough;
+	o.hex_den = 2. * COSPI_6_HOST * (n_shells + 1);
+	o.m_safe = o.mono ? (mono_ok && m_safe > 0 ? 1.0 : -1.0) : m_safe * (1.0 - eps);
+
+	std::vector<double> ec((size_t)EC_ROWS * g->nE);
+	pcb_energy_constants(d->n_energies, d->energies, d->amu, d->scatf, d->density, ec.data());
+
+	bool ok = cudaMalloc(&g->d_tables, 5 * tb) == cudaSuccess && cudaMalloc(&g->d_ec, ec.size() * 8) == cudaSuccess &&
+		  cudaMalloc(&g->d_wc, sizeof(PcbWorkCounters)) == cudaSuccess;
+	if (ok)
+		ok = cudaMemcpy(g->d_tables, h.data(), 5 * tb, cudaMemcpyHostToDevice) == cudaSuccess &&
+		     cudaMemcpy(g->d_ec, ec.data(), ec.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+	if (!ok) {
+		g_last_error = std::string("device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError());
+		pcb_gpu_optic_destroy(g);
+		return nullptr;
+	}
+	o.z = g->d_tables;
+	o.cap = g->d_tables + tn;
+	o.ext = g->d_tables + 2 * tn;
+	o.hexz = g->d_tables + 3 * tn;
+	o.rm = g->d_tables + 4 * tn;
+	o.ec = g->d_ec;
+	g->cap0 = d->cap[0];
+	g->ext0 = d->ext[0];
+	g->tables_in_smem = (5 * tb <= 160 * 1024) ? 1 : 0;
+	const char *e;
+	if ((e = getenv("POLYCAP_B200_THR_CAND"))) g->thr_cand = atoi(e);
+	if ((e = getenv("POLYCAP_B200_THR_REFL"))) g->thr_refl = atoi(e);
+	if ((e = getenv("POLYCAP_B200_THR_NEW"))) g->thr_new = atoi(e);
+	if ((e = getenv("POLYCAP_B200_CTAS_PER_SM"))) g->ctas_per_sm = atoi(e);
+	return g;
+}
+
+extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
+{
+	if (!g)
+		return;
+	cudaSetDevice(g->device);
+	cudaFree(g->d_tables); cudaFree(g->d_ec); cudaFree(g->d_wscratch); cudaFree(g->d_wc);
+	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights);
+	cudaFree(g->d_rank); cudaFree(g->d_blocksum); cudaFree(g->d_cutinfo); cudaFree(g->d_partial); cudaFree(g->d_cpartial);
+	cudaFree(g->d_rin);
+	delete g;
+}
+
+extern "C" int pcb_gpu_optic_device(const pcb_gpu_optic *g) { return g->device; }
+extern "C" int pcb_gpu_optic_n_energies(const pcb_gpu_optic *g) { return g->nE; }
+
+extern "C" void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm, int all_slow)
+{
+	if (thr_cand >= 0) g->thr_cand = thr_cand;
+	if (thr_refl >= 0) g->thr_refl = thr_refl;
+	if (thr_new >= 0) g->thr_new = thr_new;
+	if (ctas_per_sm > 0 && ctas_per_sm != g->ctas_per_sm) {
+		g->ctas_per_sm = ctas_per_sm;
+		cudaSetDevice(g->device);
+		cudaFree(g->d_wscratch);
+		g->d_wscratch = nullptr;
+	}
+	if (all_slow >= 0) g->o.all_slow = all_slow;
+}
+
+static const int TALLY_BLOCKS = 512;
+
+static int ensure_wave(pcb_gpu_optic *g, int64_t n)
+{
+	if (!g->d_wscratch) {
+		size_t slots = (size_t)g->sm_count * g->ctas_per_sm * g->threads;
+		CK(cudaMalloc(&g->d_wscratch, slots * (size_t)g->nE * 8));
+	}
+	if (n <= g->wave_cap)
+		return 0;
+	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights); cudaFree(g->d_rank);
+	g->d_status = nullptr; g->d_fields = nullptr; g->d_irefl = nullptr; g->d_weights = nullptr; g->d_rank = nullptr;
+	g->wave_cap = 0;
+	CK(cudaMalloc(&g->d_status, (size_t)n));
+	CK(cudaMalloc(&g->d_fields, (size_t)n * 17 * 8));
+	CK(cudaMalloc(&g->d_irefl, (size_t)n * 4));
+	CK(cudaMalloc(&g->d_weights, (size_t)n * g->nE * 8));
+	CK(cudaMalloc(&g->d_rank, (size_t)n * 8));
+	if (!g->d_blocksum) {
+		CK(cudaMalloc(&g->d_blocksum, (size_t)(1 << 16) * 8));
+		CK(cudaMalloc(&g->d_cutinfo, 4 * 8));
+		CK(cudaMalloc(&g->d_partial, (size_t)TALLY_BLOCKS * g->nE * 8));
+		CK(cudaMalloc(&g->d_cpartial, (size_t)TALLY_BLOCKS * 8 * 8));
+	}
+	g->wave_cap = n;
+	return 0;
+}
+
+static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n, const PcbReplayIn &rin,
+			cudaStream_t stream)
+{
+	PcbTraceParams P{};
+	P.o = g->o;
+	if (s) {
+		P.s.d_source = s->d_source; P.s.src_x = s->src_x; P.s.src_y = s->src_y; P.s.src_sigx = s->src_sigx; P.s.src_sigy = s->src_sigy;
+		P.s.src_shiftx = s->src_shiftx; P.s.src_shifty = s->src_shifty; P.s.hor_pol = s->hor_pol;
+	}
+	P.s.seed = seed;
+	P.rin = rin;
+	P.out.status = g->d_status; P.out.fields = g->d_fields; P.out.irefl = g->d_irefl; P.out.weights = g->d_weights;
+	P.wc = g->d_wc;
+	P.wscratch = g->d_wscratch;
+	P.id0 = (unsigned long long)id0;
+	P.n_ids = (unsigned long long)n;
+	P.mode = mode;
+	P.tables_in_smem = g->tables_in_smem;
+	P.thr_cand = g->thr_cand; P.thr_refl = g->thr_refl; P.thr_new = g->thr_new;
+	P.record_all = 0;
+	P.s.cap0 = g->cap0; /* uniform-illumination branch, source.c:79-89 */
+	P.s.ext0 = g->ext0;
+
+	CK(cudaMemsetAsync(g->d_wc, 0, sizeof(PcbWorkCounters), stream));
+	int blocks = g->sm_count * g->ctas_per_sm;
+	int64_t need = (n + g->threads - 1) / g->threads;
+	if (need < blocks)
+		blocks = (int)(need > 0 ? need : 1);
+	size_t smem = g->tables_in_smem ? 5 * g->table_bytes : 0;
+	if (mode == MODE_SOURCE) {
+		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_SOURCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		pcb_trace_kernel<MODE_SOURCE><<<blocks, g->threads, smem, stream>>>(P);
+	} else {
+		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		pcb_trace_kernel<MODE_REPLAY><<<blocks, g->threads, smem, stream>>>(P);
+	}
+	CK(cudaGetLastError());
+	return 0;
+}
+
+/* ------------------------------------------------------------------ replay */
+
+extern "C" int pcb_gpu_replay(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret,
+			      double *out_state, int64_t *irefl, double *weights, int64_t *counters)
+{
+	if (n <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	if (ensure_wave(g, n))
+		return -1;
+	if (n > g->replay_cap) {
+		cudaFree(g->d_rin);
+		g->d_rin = nullptr;
+		g->replay_cap = 0;
+		CK(cudaMalloc(&g->d_rin, (size_t)n * 9 * 8));
+		g->replay_cap = n;
+	}
+	cudaStream_t stream = 0;
+	CK(cudaMemcpyAsync(g->d_rin, coords, (size_t)n * 24, cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(g->d_rin + 3 * n, dir, (size_t)n * 24, cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(g->d_rin + 6 * n, ev, (size_t)n * 24, cudaMemcpyHostToDevice, stream));
+	PcbReplayIn rin{g->d_rin, g->d_rin + 3 * n, g->d_rin + 6 * n};
+	if (launch_trace(g, MODE_REPLAY, nullptr, 0, 0, n, rin, stream))
+		return -1;
+	std::vector<int8_t> st((size_t)n);
+	std::vector<int> ir((size_t)n);
+	std::vector<double> f((size_t)n * 11);
+	CK(cudaMemcpyAsync(st.data(), g->d_status, (size_t)n, cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(ir.data(), g->d_irefl, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(f.data(), g->d_fields, (size_t)n * 11 * 8, cudaMemcpyDeviceToHost, stream));
+	CK(cudaMemcpyAsync(weights, g->d_weights, (size_t)n * g->nE * 8, cudaMemcpyDeviceToHost, stream));
+	PcbWorkCounters wc;
+	CK(cudaMemcpyAsync(&wc, g->d_wc, sizeof wc, cudaMemcpyDeviceToHost, stream));
+	CK(cudaStreamSynchronize(stream));
+	for (int64_t i = 0; i < n; i++) {
+		ret[i] = st[i];
+		irefl[i] = ir[i];
+		for (int k = 0; k < 11; k++)
+			out_state[i * 11 + k] = f[(size_t)k * n + i];
+	}
+	if (counters) {
+		memset(counters, 0, PCB_C_COUNT * 8);
+		counters[PCB_C_IDS] = n;
+		counters[PCB_C_REFL_ALL] = (int64_t)wc.reflections;
+		counters[PCB_C_SEG_STEPS] = (int64_t)wc.seg_steps;
+		counters[PCB_C_SOLVES] = (int64_t)wc.solves;
+		counters[PCB_C_LAUNCHED] = (int64_t)wc.launched;
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------------ wave post-processing */
+
+static const int SCAN_T = 1024;
+
+__global__ void wave_scan_blocks(const int8_t *status, int64_t n, int64_t *rank, int64_t *blocksum)
+{
+	__shared__ int warp_tot[32];
+	int64_t i = (int64_t)blockIdx.x * SCAN_T + threadIdx.x;
+	int flag = (i < n && status[i] == ST_EXIT) ? 1 : 0;
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int v = flag;
+	for (int off = 1; off < 32; off <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, v, off);
+		if (lane >= off)
+			v += t;
+	}
+	if (lane == 31)
+		warp_tot[w] = v;
+	__syncthreads();
+	if (w == 0) {
+		int t = warp_tot[lane];
+		for (int off = 1; off < 32; off <<= 1) {
+			int u = __shfl_up_sync(0xffffffffu, t, off);
+			if (lane >= off)
+				t += u;
+		}
+		warp_tot[lane] = t;
+	}
+	__syncthreads();
+	int before = (w > 0 ? warp_tot[w - 1] : 0) + v - flag;
+	if (i < n)
+		rank[i] = before;
+	if (threadIdx.x == SCAN_T - 1)
+		blocksum[blockIdx.x] = before + flag;
+}
+
+/* single block: exclusive scan of block sums (<= 65536), total in cutinfo[2] */
+__global__ void wave_scan_sums(int64_t *blocksum, int nb, int64_t *cutinfo)
+{
+	__shared__ int64_t carry;
+	__shared__ int64_t wtot[32];
+	if (threadIdx.x == 0)
+		carry = 0;
+	__syncthreads();
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int base = 0; base < nb; base += 1024) {
+		int i = base + threadIdx.x;
+		int64_t x = (i < nb) ? blocksum[i] : 0, v = x;
+		for (int off = 1; off < 32; off <<= 1) {
+			int64_t t = __shfl_up_sync(0xffffffffu, v, off);
+			if (lane >= off)
+				v += t;
+		}
+		if (lane == 31)
+			wtot[w] = v;
+		__syncthreads();
+		if (w == 0) {
+			int64_t t = wtot[lane];
+			for (int off = 1; off < 32; off <<= 1) {
+				int64_t u = __shfl_up_sync(0xffffffffu, t, off);
+				if (lane >= off)
+					t += u;
+			}
+			wtot[lane] = t;
+		}
+		__syncthreads();
+		int64_t excl = carry + (w > 0 ? wtot[w - 1] : 0) + v - x;
+		if (i < nb)
+			blocksum[i] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023)
+			carry = excl + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		cutinfo[2] = carry;
+		cutinfo[0] = -1;
+	}
+}
+
+/* adds block offsets; finds the id just after the n_wanted-th exit */
+__global__ void wave_scan_finish(const int8_t *status, int64_t n, int64_t *rank, const int64_t *blocksum, int64_t n_wanted, int64_t *cutinfo)
+{
+	int64_t i = (int64_t)blockIdx.x * SCAN_T + threadIdx.x;
+	if (i >= n)
+		return;
+	int64_t r = rank[i] + blocksum[blockIdx.x];
+	rank[i] = r;
+	if (n_wanted > 0 && status[i] == ST_EXIT && r == n_wanted - 1)
+		cutinfo[0] = i + 1;
+}
+
+__global__ void wave_cut_resolve(int64_t n, int64_t n_wanted, int64_t *cutinfo)
+{
+	if (cutinfo[0] < 0) {
+		cutinfo[0] = n;
+		cutinfo[1] = cutinfo[2];
+	} else {
+		cutinfo[1] = n_wanted;
+	}
+}
+
+/* fixed-order partial sums: block b owns ids [b*chunk, (b+1)*chunk) below the cut */
+__global__ void wave_tally_partial(const int8_t *status, const int *irefl, const double *weights, int nE, int64_t n, const int64_t *cutinfo,
+				   double *partial, int64_t *cpartial)
+{
+	extern __shared__ double sh[];
+	const int64_t cut = cutinfo[0];
+	const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+	int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk;
+	if (hi > cut)
+		hi = cut;
+	int EW = 1;
+	while (EW < nE && EW < (int)blockDim.x)
+		EW <<= 1;
+	const int S = blockDim.x / EW;
+	const int el = threadIdx.x % EW, sub = threadIdx.x / EW;
+	for (int e0 = 0; e0 < nE; e0 += EW) {
+		int e = e0 + el;
+		double acc = 0;
+		if (e < nE)
+			for (int64_t i = lo + sub; i < hi; i += S)
+				if (status[i] == ST_EXIT)
+					acc += weights[i * nE + e];
+		sh[threadIdx.x] = acc;
+		__syncthreads();
+		if (sub == 0 && e < nE) {
+			double t = 0;
+			for (int s = 0; s < S; s++)
+				t += sh[s * EW + el];
+			partial[(size_t)blockIdx.x * nE + e] = t;
+		}
+		__syncthreads();
+	}
+	/* counters: exit, not entered, absorbed, uncounted, refl of exit photons */
+	long long c[5] = {0, 0, 0, 0, 0};
+	for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		int s = status[i];
+		if (s == ST_EXIT) {
+			c[0]++;
+			c[4] += irefl[i];
+		} else if (s == ST_NOT_ENTERED)
+			c[1]++;
+		else if (s == ST_ABSORBED)
+			c[2]++;
+		else
+			c[3]++;
+	}
+	__shared__ long long cs[5];
+	if (threadIdx.x < 5)
+		cs[threadIdx.x] = 0;
+	__syncthreads();
+	for (int k = 0; k < 5; k++) {
+		long long v = c[k];
+		for (int off = 16; off > 0; off >>= 1)
+			v += __shfl_down_sync(0xffffffffu, v, off);
+		if ((threadIdx.x & 31) == 0)
+			atomicAdd((unsigned long long *)&cs[k], (unsigned long long)v);
+	}
+	__syncthreads();
+	if (threadIdx.x < 5)
+		cpartial[(size_t)blockIdx.x * 8 + threadIdx.x] = cs[threadIdx.x];
+}
+
+__global__ void wave_tally_final(const double *partial, const int64_t *cpartial, int nb, int nE, const int64_t *cutinfo, const PcbWorkCounters *wc,
+				 double *sum_weights, int64_t *counters)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < nE) {
+		double acc = 0;
+		for (int b = 0; b < nb; b++)
+			acc += partial[(size_t)b * nE + t];
+		sum_weights[t] += acc;
+	}
+	if (t < 5) {
+		long long acc = 0;
+		for (int b = 0; b < nb; b++)
+			acc += cpartial[(size_t)b * 8 + t];
+		const int map[5] = {PCB_C_EXIT, PCB_C_NOT_ENTERED, PCB_C_NOT_TRANSMITTED, PCB_C_UNCOUNTED, PCB_C_REFL_EXIT};
+		counters[map[t]] += acc;
+	}
+	if (t == 5) {
+		counters[PCB_C_IDS] += cutinfo[0];
+		counters[PCB_C_REFL_ALL] += (int64_t)wc->reflections;
+		counters[PCB_C_SEG_STEPS] += (int64_t)wc->seg_steps;
+		counters[PCB_C_SOLVES] += (int64_t)wc->solves;
+		counters[PCB_C_LAUNCHED] += (int64_t)wc->launched;
+	}
+}
+
+/* packed records: out_fields[f][rec_base + rank], out_weights[rec_base + rank][e] */
+__global__ void wave_compact_fields(const int8_t *status, const int64_t *rank, const double *fields, int64_t n, const int64_t *cutinfo,
+				    double *out_fields, int64_t rec_cap, int64_t rec_base)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cutinfo[0] || status[i] != ST_EXIT)
+		return;
+	int64_t r = rec_base + rank[i];
+	if (r >= rec_cap)
+		return;
+#pragma unroll
+	for (int f = 0; f < 17; f++)
+		out_fields[(size_t)f * rec_cap + r] = fields[(size_t)f * n + i];
+}
+
+__global__ void wave_compact_weights(const int8_t *status, const int64_t *rank, const double *weights, int nE, int64_t n, const int64_t *cutinfo,
+				     double *out_weights, int64_t rec_cap, int64_t rec_base)
+{
+	const int lane = threadIdx.x & 31;
+	int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	const int64_t cut = cutinfo[0];
+	for (int64_t i = warp; i < cut; i += nwarps) {
+		if (status[i] != ST_EXIT)
+			continue;
+		int64_t r = rec_base + rank[i];
+		if (r >= rec_cap)
+			continue;
+		for (int e = lane; e < nE; e += 32)
+			out_weights[(size_t)r * nE + e] = weights[(size_t)i * nE + e];
+	}
+}
+
+extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
+				double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap,
+				int64_t rec_base, void *stream_v, int64_t *ids_used, int64_t *n_exit)
+{
+	cudaStream_t stream = (cudaStream_t)stream_v;
+	if (n_ids <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	if (ensure_wave(g, n_ids))
+		return -1;
+	PcbReplayIn rin{};
+	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, stream))
+		return -1;
+	g->last_wave_n = n_ids;
+	const int nb = (int)((n_ids + SCAN_T - 1) / SCAN_T);
+	if (nb > (1 << 16)) {
+		g_last_error = "wave too large (max 64M ids)";
+		return -1;
+	}
+	wave_scan_blocks<<<nb, SCAN_T, 0, stream>>>(g->d_status, n_ids, g->d_rank, g->d_blocksum);
+	wave_scan_sums<<<1, 1024, 0, stream>>>(g->d_blocksum, nb, g->d_cutinfo);
+	wave_scan_finish<<<nb, SCAN_T, 0, stream>>>(g->d_status, n_ids, g->d_rank, g->d_blocksum, n_wanted, g->d_cutinfo);
+	wave_cut_resolve<<<1, 1, 0, stream>>>(n_ids, n_wanted, g->d_cutinfo);
+	int tb = TALLY_BLOCKS;
+	if (tb > nb)
+		tb = nb;
+	wave_tally_partial<<<tb, 256, 256 * 8, stream>>>(g->d_status, g->d_irefl, g->d_weights, g->nE, n_ids, g->d_cutinfo, g->d_partial, g->d_cpartial);
+	int ft = g->nE > 6 ? g->nE : 6;
+	wave_tally_final<<<(ft + 255) / 256, 256, 0, stream>>>(g->d_partial, g->d_cpartial, tb, g->nE, g->d_cutinfo, g->d_wc, d_sum_weights, d_counters);
+	if (d_rec_fields && d_rec_weights) {
+		wave_compact_fields<<<(unsigned)((n_ids + 255) / 256), 256, 0, stream>>>(g->d_status, g->d_rank, g->d_fields, n_ids, g->d_cutinfo, d_rec_fields,
+											  rec_cap, rec_base);
+		wave_compact_weights<<<g->sm_count * 4, 256, 0, stream>>>(g->d_status, g->d_rank, g->d_weights, g->nE, n_ids, g->d_cutinfo, d_rec_weights, rec_cap,
+									  rec_base);
+	}
+	CK(cudaGetLastError());
+	if (ids_used || n_exit) {
+		int64_t ci[3];
+		CK(cudaMemcpyAsync(ci, g->d_cutinfo, sizeof ci, cudaMemcpyDeviceToHost, stream));
+		CK(cudaStreamSynchronize(stream));
+		if (ids_used)
+			*ids_used = ci[0];
+		if (n_exit)
+			*n_exit = ci[1];
+	}
+	return 0;
+}
+
+extern "C" int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, double *rec)
+{
+	CK(cudaSetDevice(g->device));
+	if (n_ids > g->last_wave_n) {
+		g_last_error = "no such wave";
+		return -1;
+	}
+	CK(cudaDeviceSynchronize());
+	CK(cudaMemcpy(status, g->d_status, (size_t)n_ids, cudaMemcpyDeviceToHost));
+	if (rec) {
+		const int64_t n = g->last_wave_n;
+		std::vector<double> f((size_t)n * 17), w((size_t)n_ids * g->nE);
+		CK(cudaMemcpy(f.data(), g->d_fields, f.size() * 8, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(w.data(), g->d_weights, w.size() * 8, cudaMemcpyDeviceToHost));
+		const size_t stride = 17 + g->nE;
+		for (int64_t i = 0; i < n_ids; i++) {
+			for (int k = 0; k < 17; k++)
+				rec[i * stride + k] = f[(size_t)k * n + i];
+			memcpy(rec + i * stride + 17, w.data() + (size_t)i * g->nE, (size_t)g->nE * 8);
+		}
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------------ small device helpers */
+
+extern "C" void *pcb_gpu_malloc(int device, size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaSetDevice(pick_device(device)) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess) {
+		g_last_error = "cudaMalloc failed";
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void pcb_gpu_free(int device, void *p)
+{
+	cudaSetDevice(pick_device(device));
+	cudaFree(p);
+}
+extern "C" int pcb_gpu_memset(int device, void *p, int v, size_t bytes, void *stream)
+{
+	CK(cudaSetDevice(pick_device(device)));
+	CK(cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream));
+	return 0;
+}
+extern "C" int pcb_gpu_copy_to_host(int device, void *dst, const void *src, size_t bytes, void *stream)
+{
+	CK(cudaSetDevice(pick_device(device)));
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+extern "C" int pcb_gpu_sync(int device, void *stream)
+{
+	CK(cudaSetDevice(pick_device(device)));
+	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+
+/* ------------------------------------------------------------------ FP64 peak */
+
+__global__ void dfma_peak_kernel(double *out, int iters)
+{
+	double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double m = 1.0000001, c = 1e-9;
+	for (int i = 0; i < iters; i++) {
+		a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+		a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+	}
+	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" double pcb_gpu_dfma_peak(int device, int iters)
+{
+	device = pick_device(device);
+	if (cudaSetDevice(device) != cudaSuccess)
+		return -1;
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	int blocks = prop.multiProcessorCount * 8, threads = 256;
+	double *d = nullptr;
+	if (cudaMalloc(&d, (size_t)blocks * threads * 8) != cudaSuccess)
+		return -1;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	dfma_peak_kernel<<<blocks, threads>>>(d, iters / 4 + 1);
+	double best = 0;
+	for (int rep = 0; rep < 3; rep++) {
+		cudaEventRecord(e0);
+		dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+		cudaEventRecord(e1);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+		if (tf > best)
+			best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	return best;
+}
