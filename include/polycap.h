@@ -2,7 +2,7 @@
  * include/polycap.h -- the drop-in C boundary of polycap-b200.
  *
  * One self-contained header declaring the complete public C API of polycap 1.2, so that the
- * reference's CLI (src/main.c), its Cython wrapper (python/*.pxd) and user code compile and
+ * reference's CLI (src/main.c), its Cython wrapper (python .pxd files) and user code compile and
  * link against libpolycap_b200.so unchanged.  Every prototype below cites the reference
  * declaration it replaces (paths relative to the reference tree).  Signatures, return codes,
  * ownership and error conventions are those of the reference; what differs is that the

@@ -92,7 +92,7 @@ __device__ __forceinline__ void hex_cell(double hexz, double x, double y, double
 /* ------------------------------------------------------------------ ray / truncated-cone solve
  * capil.c:105-254 (argument checks of :65-100 are done by the callers that can violate them).
  * `last_z` is photon_coord->z on entry.  Returns the reference's code; on 1 fills hit and sn. */
-__device__ __noinline__ int segment_solve(const V3 &c0, const V3 &c1, double r0, double r1, const V3 &p0, V3 dir, double last_z, V3 &hit, V3 &sn)
+static __device__ __noinline__ int segment_solve(const V3 &c0, const V3 &c1, double r0, double r1, const V3 &p0, V3 dir, double last_z, V3 &hit, V3 &sn)
 {
 	sn.x = sn.y = sn.z = 0.0;
 	norm3(dir);
@@ -262,7 +262,7 @@ struct ReflGeom {
 	V3 new_ev;
 };
 
-__device__ __noinline__ void refl_geometry(V3 sn, const V3 &dir, V3 &ev, ReflGeom &g)
+static __device__ __noinline__ void refl_geometry(V3 sn, const V3 &dir, V3 &ev, ReflGeom &g)
 {
 	if (sqrt(sn.x * sn.x + sn.y * sn.y + sn.z * sn.z) != 1)
 		norm3(sn);
@@ -340,7 +340,7 @@ struct StartState {
 	double src_x, src_y;
 };
 
-__device__ __noinline__ void source_sample(const PcbSource &s, int mono, uint64_t id, StartState &o)
+static __device__ __noinline__ void source_sample(const PcbSource &s, int mono, uint64_t id, StartState &o)
 {
 	Philox rng;
 	rng.init(s.seed, id);

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cinttypes>
+#include <ctime>
 
 #include "pcb_internal.h"
 #include "optconst.h"
