@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- photons/s and reflections/s of the photon-transport hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload conical|xos1|ellip]
+
+Workload (N=1 default, BASELINE.json configs[1] / SURVEY 8d C2): conical polycapillary
+(POLYCAP_PROFILE_CONICAL, radii of example/cone.*), 200000 capillaries, SiO2, source at 100 cm,
+10-energy grid 1..30 keV; one STEP = one pass of the hot path over a batch of 1e7 photon ids per GPU
+(source sampling with Philox4x32-10 per id -> hexagonal lookup -> segment scan -> reflection loop with the
+per-energy Fresnel weight update -> device-resident tallies).  "photons" are counted the way the reference
+counts "Simulated photons" (iexit + not_entered + not_transmitted, /root/reference/src/polycap-source.c:1061).
+
+  value      device-timed (CUDA events, max over ranks), everything resident in HBM, whole job over N GPUs
+  e2e        the same metric through the reference-facing C-ABI call polycap_source_get_transmission_efficiencies
+             with HOST buffers: table upload (H2D) and exit-record download (D2H) inside the timed region
+  roofline   FP64-pipe bound: algorithmic flops (SURVEY 8d model x device work counters) / trace-kernel time
+             (CUDA events on its stream) against an in-run DFMA peak measurement; an HBM line is given as well
+  cpu_baseline / --impl reference: the reference's own OpenMP path (oracle/_ref, its sources compiled in place)
+             on the box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIO2 = {8: 53.0, 14: 47.0}
+WORKLOADS = {
+    # name: (profile args, n_cap, sig_rough, source args, energies, ids per step per GPU)
+    "conical": dict(profile=(0, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5), n_cap=200000, sig_rough=0.0,
+                    source=(100.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.0), energies=np.linspace(1, 30, 10), ids=10_000_000,
+                    desc="conical polycap (POLYCAP_PROFILE_CONICAL, cone.* radii), 1e7 photon ids/step/GPU, 10-energy grid 1-30 keV"),
+    "ellip": dict(profile=(2, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5), n_cap=200000, sig_rough=0.0,
+                  source=(2000.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.0), energies=np.linspace(1, 40, 400), ids=1_000_000,
+                  desc="ellipsoidal polycap (ellip_l9 geometry), 1e6 photon ids/step/GPU, 400-energy grid 1-40 keV, leaks off"),
+    "xos1": dict(profile=(2, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5), n_cap=200000, sig_rough=0.0,
+                 source=(2000.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.0), energies=1.0 + 0.1 * np.arange(291), ids=2_000_000,
+                 desc="XOS-like ellipsoidal profile, 2e6 photon ids/step/GPU, 291-energy grid 1-30 keV (xos1.inp grid)"),
+}
+
+# algorithmic FP64 flops of the minimal result-equivalent algorithm
+F_LAUNCH, F_STEP, F_REFL, F_FRESNEL, F_EXIT = 155, 24, 445, 70, 100
+
+
+def algorithmic_flops(cnt, nE):
+    return (F_LAUNCH * cnt["launched"] + F_STEP * cnt["seg_steps"] + F_REFL * cnt["refl_all"] + F_FRESNEL * nE * cnt["refl_all"]
+            + F_EXIT * cnt["exit"])
+
+
+@contextlib.contextmanager
+def quiet_stdout():
+    """the C libraries printf their run summaries (source.c:1061-1063); keep stdout to the one JSON line"""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline (oracle/_ref)
+def reference_setup(w):
+    from oracle import harness as H
+    if not H.ref_available():
+        raise RuntimeError("oracle/_ref/libpolycap_ref.so is missing (built by oracle/Makefile where /root/reference exists)")
+    ref = H.Ref()
+    L = ref.L
+    prof = L.polycap_profile_new(*w["profile"], None)
+    desc = ref.description(prof, w["sig_rough"], w["n_cap"], list(SIO2.keys()), list(SIO2.values()), 2.23)
+    src = ref.source(desc, *w["source"], w["energies"])
+    return ref, src
+
+
+def reference_run(ref, src, n_exit, threads=-1):
+    """one call of the reference's own polycap_source_get_transmission_efficiencies; returns (seconds, started, exits, reflections)"""
+    with quiet_stdout():
+        t0 = time.perf_counter()
+        eff = ref.L.polycap_source_get_transmission_efficiencies(src, threads, int(n_exit), False, None, None)
+        dt = time.perf_counter() - t0
+    im = eff.contents.images.contents
+    started, exits = im.i_start, im.i_exit
+    refl = int(np.ctypeslib.as_array(im.pc_exit_nrefl, (exits,)).sum())
+    ref.L.polycap_transmission_efficiencies_free(eff)
+    return dt, started, exits, refl
+
+
+def reference_sample(w, seconds, steps=1, warmup=0):
+    """bounded sample: n_exit sized from a probe so that one call takes about `seconds`"""
+    ref, src = reference_setup(w)
+    cores = os.cpu_count() or 1
+    dt, started, exits, _ = reference_run(ref, src, 40)
+    n = max(40, int(40 * seconds / max(dt, 1e-3)))
+    for _ in range(warmup):
+        reference_run(ref, src, max(40, n // 4))
+    tot_t = tot_started = tot_refl = tot_exit = 0
+    for _ in range(steps):
+        dt, started, exits, refl = reference_run(ref, src, n)
+        tot_t += dt; tot_started += started; tot_refl += refl; tot_exit += exits
+    ref.L.polycap_source_free(src)
+    return dict(value=tot_started / tot_t, unit="photons/s", cores=cores, kind="reference",
+                sample="%d call(s) of the reference's polycap_source_get_transmission_efficiencies (oracle/_ref: its own sources, gcc -O2 -fopenmp, "
+                       "xraylib replaced by the built-in optical-constants table => per-photon scatf is cheaper than with real xraylib), "
+                       "n_photons=%d exits/call = %d simulated photons in %.1f s on %d host threads" % (steps, n, tot_started, tot_t, cores),
+                exit_photons_per_s=tot_exit / tot_t, reflections_of_exit_photons_per_s=tot_refl / tot_t, ms_per_step=1e3 * tot_t / steps)
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="conical", choices=sorted(WORKLOADS))
+    ap.add_argument("--ids", type=int, default=0, help="photon ids per step per GPU (default: the workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    nE = len(w["energies"])
+    ids_per_step = args.ids or w["ids"]
+    config = {"workload": w["desc"] if not args.ids else w["desc"] + " [ids/step/GPU overridden: %d]" % ids_per_step,
+              "n_energies": nE, "photon_ids_per_step_per_gpu": ids_per_step, "sharding": "contiguous photon-id ranges, 1 rank per GPU",
+              "l2": "flushed between timed steps (256 MiB write); every step traces fresh ids"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        per_step = max(3.0, min(20.0, 120.0 / (steps + 0.25 * args.warmup + 0.5)))
+        b = reference_sample(w, per_step, steps=steps, warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "photons/s", "value": b["value"], "unit": "photons/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": b["value"], "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "exit_photons_per_s": b["exit_photons_per_s"], "reflections_of_exit_photons_per_s": b["reflections_of_exit_photons_per_s"]}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import polycap_b200 as pc
+    from polycap_b200.distributed import shard_range, allreduce_tallies
+
+    if not torch.cuda.is_available() or pc.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    prof = pc.Profile(*w["profile"])
+    desc = pc.Description(prof, w["sig_rough"], w["n_cap"], SIO2, 2.23)
+    src = pc.Source(desc, *w["source"], w["energies"])
+    seed = 20000
+    ses = pc.Session(src, device=local_rank, seed=seed)
+    ses.timing(True)
+    t_sum = torch.zeros(nE, dtype=torch.float64, device=dev)
+    t_cnt = torch.zeros(pc.N_COUNTERS, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(k):
+        """one pass over this rank's shard of step k's ids (weak scaling: ids_per_step per GPU)"""
+        lo, hi = shard_range(ids_per_step * world, rank, world, id0=k * ids_per_step * world)
+        ses.run(lo, hi - lo, t_sum.data_ptr(), t_cnt.data_ptr(), wave_size=ids_per_step, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    ses.trace_ms()  # drop warm-up timings
+    k0_kernels = ses.kernels()
+    t_sum.zero_(); t_cnt.zero_()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)  # L2 flush, outside the event pair
+        ev[k][0].record()
+        step(args.warmup + k)
+        ev[k][1].record()
+    allreduce_tallies(t_sum, t_cnt)  # the one collective of the path (NCCL over NVLink when world > 1)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
+    total_ms = step_ms.sum().reshape(1)
+    trace_ms, trace_launches = ses.trace_ms()
+    trace = torch.tensor([trace_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(trace, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    cnt = dict(zip(pc.COUNTER_NAMES, t_cnt.cpu().tolist()))
+    sw = t_sum.cpu().numpy()
+    photons = cnt["exit"] + cnt["not_entered"] + cnt["not_transmitted"]
+    kernels = ses.kernels()
+
+    # ---- e2e through the reference-facing call, host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        exit_frac = max(cnt["exit"] / max(cnt["ids"], 1), 1e-6)
+        n_exit = max(1000, int(exit_frac * ids_per_step))
+        n_exit = min(n_exit, 2_000_000_000 // (8 * (17 + nE)))
+        os.environ["POLYCAP_B200_DEVICE"] = str(local_rank)
+        os.environ["POLYCAP_B200_NO_CACHE"] = "1"
+        os.environ["POLYCAP_B200_SEED"] = "777"
+        with quiet_stdout():
+            src.get_transmission_efficiencies(-1, max(1000, n_exit // 10))  # warm-up of the API path
+            barrier()
+            t0 = time.perf_counter()
+            reps = max(1, min(args.steps, 3))
+            for _ in range(reps):
+                e2e_last = src.get_transmission_efficiencies(-1, n_exit)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        # simulated photons: i_start of the result object (same seed => every call simulates the same photons)
+        import ctypes as C
+
+        class _Im(C.Structure):
+            _fields_ = [("i_start", C.c_int64), ("i_exit", C.c_int64)]
+
+        class _Te(C.Structure):
+            _fields_ = [("n_energies", C.c_size_t), ("energies", C.c_void_p), ("efficiencies", C.c_void_p), ("images", C.POINTER(_Im))]
+        i_start = C.cast(e2e_last._trans_eff, C.POINTER(_Te)).contents.images.contents.i_start
+        t_e2e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        n_e2e = torch.tensor([i_start * reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+            dist.all_reduce(n_e2e, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(n_e2e.item() / t_e2e.item()), "unit": "photons/s",
+               "h2d_bytes_per_step": int(5 * 8 * 1002 + 6 * 8 * nE), "d2h_bytes_per_step": int(n_exit * 8 * (17 + nE) + 8 * nE + 8 * pc.N_COUNTERS),
+               "call": "polycap_source_get_transmission_efficiencies(source, -1, n_photons=%d exits) x %d, tables re-uploaded per call "
+                       "(POLYCAP_B200_NO_CACHE), exit records returned in host arrays" % (n_exit, reps),
+               "simulated_photons_per_call": int(i_start), "seconds": float(t_e2e.item())}
+        del os.environ["POLYCAP_B200_NO_CACHE"]
+
+    if rank == 0:
+        flops = algorithmic_flops(cnt, nE)
+        trace_s = float(trace.item()) * 1e-3
+        dfma_peak = pc.dfma_peak_tflops(local_rank, 400000)
+        peaks = measured_peaks()
+        hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+        rec_bytes = cnt["exit"] * 8 * (17 + nE) * 2 + cnt["ids"] * (1 + 4 + 8)  # dense exit records written + re-read by the tally; status/irefl/rank per id
+        # per GPU: rank 0's trace time over rank 0's share of the work (weak scaling: equal shares)
+        achieved_tf = flops / world / trace_s / 1e12 if trace_s > 0 else 0.0
+        line = {
+            "metric": "photons/s", "value": photons / total_s, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config,
+            "reflections_per_s": cnt["refl_all"] / total_s, "exit_photons_per_s": cnt["exit"] / total_s, "photon_ids_per_s": cnt["ids"] / total_s,
+            "reflections_of_exit_photons_per_s": cnt["refl_exit"] / total_s,
+            "counters": cnt, "efficiencies": (sw / max(photons, 1)).tolist(),
+            "gpu_launches": int(kernels[0] - k0_kernels[0]), "trace_kernel_launches": int(trace_launches),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak if dfma_peak > 0 else None,
+                         "traffic": None, "kernel": "pcb_trace_kernel<MODE_SOURCE>", "kernel_ms_per_launch": 1e3 * trace_s / max(trace_launches, 1),
+                         "kernel_share_of_step": trace_s / total_s if total_s > 0 else None,
+                         "algorithmic_flops_per_launch": flops / world / max(trace_launches, 1),
+                         "model": "155*launched + 24*seg_steps + 445*refl + 70*nE*refl + 100*exit (SURVEY 8d)",
+                         "peak_source": "DFMA microbenchmark run on this GPU inside bench.py (polycap_b200_dfma_peak_tflops); MEASURED_PEAKS.json holds no FP64 figure",
+                         "hbm": {"achieved": rec_bytes / world / trace_s / 1e9 if trace_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}},
+            "clocks": clocks, "optical_constants": pc.optconst_provider(),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                b = reference_sample(w, args.cpu_seconds)
+                line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as exc:  # the checker is optional infrastructure; the GPU numbers stand without it
+                line["cpu_baseline"] = {"value": None, "unit": "photons/s", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % exc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -79,6 +79,13 @@ POLYCAP_EXTERN bool polycap_b200_session_run(polycap_b200_session *session, int6
 /* phase-vote thresholds (lanes) and resident CTAs per SM of the tracer; negative keeps the current value */
 POLYCAP_EXTERN void polycap_b200_session_tune(polycap_b200_session *session, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm);
 
+/* Instrumentation for benchmarks.  _timing(on): bracket every trace-kernel launch with CUDA events on its stream.
+ * _trace_ms: waits for the timed launches since the last call, returns their summed device time [ms] and count.
+ * _kernels: kernels this session has launched so far (all of them / trace kernels only). */
+POLYCAP_EXTERN void polycap_b200_session_timing(polycap_b200_session *session, int on);
+POLYCAP_EXTERN double polycap_b200_session_trace_ms(polycap_b200_session *session, int64_t *n_launches);
+POLYCAP_EXTERN int64_t polycap_b200_session_kernels(polycap_b200_session *session, int64_t *n_trace_kernels);
+
 /* FP64 FMA throughput of `device` in TFLOP/s (2 flops per DFMA) -- the roofline denominator */
 POLYCAP_EXTERN double polycap_b200_dfma_peak_tflops(int device, int iters);
 

@@ -115,6 +115,9 @@ _session_new = _sig("polycap_b200_session_new", _v, [_v, C.c_int, C.c_uint64, _E
 _session_free = _sig("polycap_b200_session_free", None, [_v])
 _session_run = _sig("polycap_b200_session_run", C.c_bool, [_v, C.c_int64, C.c_int64, C.c_int64, _v, _v, _v, _ErrPP])
 _session_tune = _sig("polycap_b200_session_tune", None, [_v, C.c_int, C.c_int, C.c_int, C.c_int])
+_session_timing = _sig("polycap_b200_session_timing", None, [_v, C.c_int])
+_session_trace_ms = _sig("polycap_b200_session_trace_ms", C.c_double, [_v, c_int64_p])
+_session_kernels = _sig("polycap_b200_session_kernels", C.c_int64, [_v, c_int64_p])
 _dfma_peak = _sig("polycap_b200_dfma_peak_tflops", C.c_double, [C.c_int, C.c_int])
 
 
@@ -619,6 +622,21 @@ class Session:
         e = _err()
         _session_run(self._session, int(id0), int(n_ids), int(wave_size), C.c_void_p(stream), C.c_void_p(d_sum_weights), C.c_void_p(d_counters), C.byref(e))
         _raise(e)
+
+    def timing(self, on=True):
+        _session_timing(self._session, 1 if on else 0)
+
+    def trace_ms(self):
+        """(summed device ms, launches) of the trace kernels timed since the last call; synchronises on them"""
+        n = C.c_int64(0)
+        ms = _session_trace_ms(self._session, C.byref(n))
+        return ms, n.value
+
+    def kernels(self):
+        """(all kernels, trace kernels) launched by this session so far"""
+        n = C.c_int64(0)
+        tot = _session_kernels(self._session, C.byref(n))
+        return tot, n.value
 
     def tune(self, thr_cand=-1, thr_refl=-1, thr_new=-1, ctas_per_sm=-1):
         _session_tune(self._session, thr_cand, thr_refl, thr_new, ctas_per_sm)

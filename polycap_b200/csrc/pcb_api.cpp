@@ -91,8 +91,9 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 	h = fnv(h, scatf.data(), nE * 8);
 	h = fnv(h, &device, sizeof device);
 	CachedOptic *slot = &g_cache[0];
+	const bool no_cache = getenv("POLYCAP_B200_NO_CACHE") != NULL; /* re-upload the tables on every call (end-to-end timing) */
 	for (auto &c : g_cache) {
-		if (c.g && c.key == h) {
+		if (c.g && c.key == h && !no_cache) {
 			c.stamp = ++g_stamp;
 			return c.g;
 		}
@@ -1356,6 +1357,23 @@ extern "C" void polycap_b200_session_tune(polycap_b200_session *session, int thr
 		return;
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
 	pcb_gpu_optic_tune(session->g, thr_cand, thr_refl, thr_new, ctas_per_sm, -1);
+}
+
+extern "C" void polycap_b200_session_timing(polycap_b200_session *session, int on)
+{
+	if (session)
+		pcb_gpu_optic_timing(session->g, on);
+}
+extern "C" double polycap_b200_session_trace_ms(polycap_b200_session *session, int64_t *n_launches)
+{
+	if (!session)
+		return 0;
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	return pcb_gpu_optic_trace_ms(session->g, n_launches);
+}
+extern "C" int64_t polycap_b200_session_kernels(polycap_b200_session *session, int64_t *n_trace_kernels)
+{
+	return session ? pcb_gpu_optic_kernels(session->g, n_trace_kernels) : 0;
 }
 
 extern "C" double polycap_b200_dfma_peak_tflops(int device, int iters) { return pcb_gpu_dfma_peak(device, iters > 0 ? iters : 200000); }

@@ -55,6 +55,11 @@ int pcb_gpu_optic_n_energies(const pcb_gpu_optic *g);
 /* Tuning knobs (phase-vote thresholds in lanes, CTAs per SM, exact-check mode); <0 keeps the default. */
 void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm, int all_slow);
 
+/* instrumentation (bench.py): CUDA-event timing of the trace kernels, kernel-launch counts */
+void pcb_gpu_optic_timing(pcb_gpu_optic *g, int on);
+int64_t pcb_gpu_optic_kernels(const pcb_gpu_optic *g, int64_t *n_trace);
+double pcb_gpu_optic_trace_ms(pcb_gpu_optic *g, int64_t *n_launches);
+
 /* Replay: n start states in host memory -> per-photon results in host memory.
  * out_state: [n][11] = exit coords(3), exit dir(3), exit elecv(3), d_travel, capil_trace calls */
 int pcb_gpu_replay(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state,

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pcb_gpu.h"
@@ -81,6 +82,13 @@ struct pcb_gpu_optic {
 	/* replay buffers */
 	int64_t replay_cap = 0;
 	double *d_rin = nullptr;
+	/* instrumentation: kernels launched, and (when timing is on) CUDA-event pairs around every trace kernel */
+	int64_t n_kernels = 0, n_trace = 0;
+	int timing = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending;
+	std::vector<cudaEvent_t> ev_pool;
+	double trace_ms = 0;
+	int64_t trace_timed = 0;
 };
 
 static int pick_device(int device)
@@ -209,7 +217,55 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights);
 	cudaFree(g->d_rank); cudaFree(g->d_blocksum); cudaFree(g->d_cutinfo); cudaFree(g->d_partial); cudaFree(g->d_cpartial);
 	cudaFree(g->d_rin);
+	for (auto &p : g->ev_pending) {
+		cudaEventDestroy(p.first);
+		cudaEventDestroy(p.second);
+	}
+	for (auto &e : g->ev_pool)
+		cudaEventDestroy(e);
 	delete g;
+}
+
+/* ---- instrumentation ---- */
+extern "C" void pcb_gpu_optic_timing(pcb_gpu_optic *g, int on) { g->timing = on; }
+extern "C" int64_t pcb_gpu_optic_kernels(const pcb_gpu_optic *g, int64_t *n_trace)
+{
+	if (n_trace)
+		*n_trace = g->n_trace;
+	return g->n_kernels;
+}
+/* total device time of the trace kernels launched since the last call (ms) and how many; waits for them */
+extern "C" double pcb_gpu_optic_trace_ms(pcb_gpu_optic *g, int64_t *n_launches)
+{
+	cudaSetDevice(g->device);
+	for (auto &p : g->ev_pending) {
+		float ms = 0;
+		cudaEventSynchronize(p.second);
+		if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) {
+			g->trace_ms += ms;
+			g->trace_timed++;
+		}
+		g->ev_pool.push_back(p.first);
+		g->ev_pool.push_back(p.second);
+	}
+	g->ev_pending.clear();
+	double t = g->trace_ms;
+	if (n_launches)
+		*n_launches = g->trace_timed;
+	g->trace_ms = 0;
+	g->trace_timed = 0;
+	return t;
+}
+static cudaEvent_t take_event(pcb_gpu_optic *g)
+{
+	cudaEvent_t e;
+	if (!g->ev_pool.empty()) {
+		e = g->ev_pool.back();
+		g->ev_pool.pop_back();
+		return e;
+	}
+	cudaEventCreate(&e);
+	return e;
 }
 
 extern "C" int pcb_gpu_optic_device(const pcb_gpu_optic *g) { return g->device; }
@@ -286,12 +342,24 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 	if (need < blocks)
 		blocks = (int)(need > 0 ? need : 1);
 	size_t smem = g->tables_in_smem ? 5 * g->table_bytes : 0;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (g->timing) {
+		e0 = take_event(g);
+		e1 = take_event(g);
+		cudaEventRecord(e0, stream);
+	}
+	g->n_kernels++;
+	g->n_trace++;
 	if (mode == MODE_SOURCE) {
 		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_SOURCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		pcb_trace_kernel<MODE_SOURCE><<<blocks, g->threads, smem, stream>>>(P);
 	} else {
 		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		pcb_trace_kernel<MODE_REPLAY><<<blocks, g->threads, smem, stream>>>(P);
+	}
+	if (g->timing) {
+		cudaEventRecord(e1, stream);
+		g->ev_pending.emplace_back(e0, e1);
 	}
 	CK(cudaGetLastError());
 	return 0;
@@ -600,7 +668,9 @@ extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint
 	wave_tally_partial<<<tb, 256, 256 * 8, stream>>>(g->d_status, g->d_irefl, g->d_weights, g->nE, n_ids, g->d_cutinfo, g->d_partial, g->d_cpartial);
 	int ft = g->nE > 6 ? g->nE : 6;
 	wave_tally_final<<<(ft + 255) / 256, 256, 0, stream>>>(g->d_partial, g->d_cpartial, tb, g->nE, g->d_cutinfo, g->d_wc, d_sum_weights, d_counters);
+	g->n_kernels += 6;
 	if (d_rec_fields && d_rec_weights) {
+		g->n_kernels += 2;
 		wave_compact_fields<<<(unsigned)((n_ids + 255) / 256), 256, 0, stream>>>(g->d_status, g->d_rank, g->d_fields, n_ids, g->d_cutinfo, d_rec_fields,
 											  rec_cap, rec_base);
 		wave_compact_weights<<<g->sm_count * 4, 256, 0, stream>>>(g->d_status, g->d_rank, g->d_weights, g->nE, n_ids, g->d_cutinfo, d_rec_weights, rec_cap,
