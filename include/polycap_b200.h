@@ -64,6 +64,10 @@ POLYCAP_EXTERN bool polycap_b200_photon_launch_batch(polycap_description *descri
 POLYCAP_EXTERN bool polycap_b200_source_run_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, bool leak_calc,
 						double *sum_weights, int64_t *counters, int8_t *status, double *rec, polycap_error **error);
 
+/* The start state (source.c:23-144 over the id's Philox stream) the device draws for ids [id0, id0+n_ids):
+ * out[n_ids][11] = start coords(3), start direction(3), electric vector(3), source point x, y. */
+POLYCAP_EXTERN bool polycap_b200_source_sample_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, double *out, polycap_error **error);
+
 /* ---- sessions: device-resident tallies for benchmarks and multi-GPU reductions -------------- */
 typedef struct _polycap_b200_session polycap_b200_session;
 

@@ -274,8 +274,20 @@ class Oracle:
         L.orc_philox_uniform.restype = C.c_double
         L.orc_philox_uniform.argtypes = [C.c_void_p]
         L.orc_philox4x32_10.argtypes = [P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]
+        L.orc_run_starts.argtypes = [P(OrcOptic), C.c_int64, c_double_p, C.c_int, C.c_int, c_double_p, P(OrcCounters), P(C.c_int8), c_double_p]
         L.orc_run_ids.argtypes = [P(OrcSource), P(OrcOptic), C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                   c_double_p, P(OrcCounters), P(C.c_int8), c_double_p]
+
+    def run_starts(self, optic, starts, leak=False, threads=1, records=False):
+        starts = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 11)
+        n, nE = starts.shape[0], optic.nE
+        sw = np.zeros(nE)
+        cnt = OrcCounters()
+        status = np.zeros(n, dtype=np.int8)
+        rec = np.zeros((n, 17 + nE)) if records else None
+        self.L.orc_run_starts(C.byref(optic.c), n, starts.ctypes.data_as(c_double_p), int(leak), threads, sw.ctypes.data_as(c_double_p),
+                              C.byref(cnt), status.ctypes.data_as(C.POINTER(C.c_int8)), rec.ctypes.data_as(c_double_p) if records else None)
+        return sw, {n_: getattr(cnt, n_) for n_, _ in OrcCounters._fields_}, status, rec
 
     def photon(self, optic, start, direction, elecv):
         ph = OrcPhoton()

@@ -954,8 +954,24 @@ double orc_philox_uniform(void *state)
 
 /* ------------------------------------------------------------------ driver */
 
+static void run_ids_impl(const orc_source *s, const orc_optic *o, uint64_t seed, int64_t id0, int64_t n_ids, int leak_calc, int threads,
+			 double *sum_weights, orc_counters *cnt, int8_t *status, double *rec, const double *starts);
+
 void orc_run_ids(const orc_source *s, const orc_optic *o, uint64_t seed, int64_t id0, int64_t n_ids, int leak_calc,
-		 int threads, double *sum_weights, orc_counters *cnt, int8_t *status, double *rec) /* source.c:745-1075 */
+		 int threads, double *sum_weights, orc_counters *cnt, int8_t *status, double *rec)
+{
+	run_ids_impl(s, o, seed, id0, n_ids, leak_calc, threads, sum_weights, cnt, status, rec, NULL);
+}
+
+/* same driver over caller-supplied start states starts[n][11] = coords(3) dir(3) elecv(3) src_x src_y instead of sampling them */
+void orc_run_starts(const orc_optic *o, int64_t n, const double *starts, int leak_calc, int threads, double *sum_weights, orc_counters *cnt,
+		    int8_t *status, double *rec)
+{
+	run_ids_impl(NULL, o, 0, 0, n, leak_calc, threads, sum_weights, cnt, status, rec, starts);
+}
+
+static void run_ids_impl(const orc_source *s, const orc_optic *o, uint64_t seed, int64_t id0, int64_t n_ids, int leak_calc, int threads,
+			 double *sum_weights, orc_counters *cnt, int8_t *status, double *rec, const double *starts) /* source.c:745-1075 */
 {
 	size_t nE = o->n_energies;
 	int nm = o->nmax;
@@ -980,8 +996,17 @@ void orc_run_ids(const orc_source *s, const orc_optic *o, uint64_t seed, int64_t
 			orc_photon ph;
 			memset(&ph, 0, sizeof ph);
 			ph.weight = w;
-			orc_philox_stream st = {seed, (uint64_t)(id0 + j), 0};
-			orc_source_get_photon(s, o, orc_philox_uniform, &st, &ph);
+			if (starts) {
+				const double *q = starts + (size_t)j * 11;
+				orc_vec3 c = {q[0], q[1], q[2]}, d = {q[3], q[4], q[5]}, e = {q[6], q[7], q[8]}, sp = {q[9], q[10], 0};
+				ph.start_coords = ph.exit_coords = c;
+				ph.start_direction = ph.exit_direction = d;
+				ph.start_electric_vector = ph.exit_electric_vector = e;
+				ph.src_start_coords = sp;
+			} else {
+				orc_philox_stream st = {seed, (uint64_t)(id0 + j), 0};
+				orc_source_get_photon(s, o, orc_philox_uniform, &st, &ph);
+			}
 			int iesc = orc_photon_launch(o, &ph, leak_calc);
 			int code = iesc;
 			if (iesc == 1) { /* exit-window test, source.c:762-777 */

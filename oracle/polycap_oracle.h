@@ -116,6 +116,10 @@ typedef struct {
 void orc_run_ids(const orc_source *s, const orc_optic *o, uint64_t seed, int64_t id0, int64_t n_ids,
 		 int leak_calc, int threads, double *sum_weights, orc_counters *cnt, int8_t *status, double *rec);
 
+/* the same driver over caller-supplied start states starts[n][11] = coords(3) dir(3) elecv(3) src_x src_y */
+void orc_run_starts(const orc_optic *o, int64_t n, const double *starts, int leak_calc, int threads, double *sum_weights, orc_counters *cnt,
+		    int8_t *status, double *rec);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,7 @@ _launch_batch = _sig("polycap_b200_photon_launch_batch", C.c_bool,
                       C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_int64_p, _ErrPP])
 _run_ids = _sig("polycap_b200_source_run_ids", C.c_bool,
                 [_v, C.c_uint64, C.c_int64, C.c_int64, C.c_bool, c_double_p, c_int64_p, C.POINTER(C.c_int8), c_double_p, _ErrPP])
+_sample_ids = _sig("polycap_b200_source_sample_ids", C.c_bool, [_v, C.c_uint64, C.c_int64, C.c_int64, c_double_p, _ErrPP])
 _session_new = _sig("polycap_b200_session_new", _v, [_v, C.c_int, C.c_uint64, _ErrPP])
 _session_free = _sig("polycap_b200_session_free", None, [_v])
 _session_run = _sig("polycap_b200_session_run", C.c_bool, [_v, C.c_int64, C.c_int64, C.c_int64, _v, _v, _v, _ErrPP])
@@ -562,6 +563,14 @@ class Source:
         class _S(C.Structure):  # head of struct _polycap_source (private.h:108-122)
             _fields_ = [("description", _v), ("rng", _v)] + [(k, C.c_double) for k in "abcdefgh"] + [("n_energies", C.c_size_t)]
         return C.cast(self._source, C.POINTER(_S)).contents.n_energies
+
+    def sample_ids(self, seed, id0, n_ids):
+        """start states the device draws for ids [id0, id0+n_ids): [n][11] = coords, direction, elecv, source x, y"""
+        out = np.zeros((n_ids, 11))
+        e = _err()
+        _sample_ids(self._source, seed, id0, n_ids, _dp(out), C.byref(e))
+        _raise(e)
+        return out
 
     def run_ids(self, seed, id0, n_ids, records=False, status=True):
         """Photon ids [id0, id0+n_ids) with Philox seed `seed`: (sum_weights, counters dict, status, rec)"""

@@ -1284,6 +1284,27 @@ extern "C" bool polycap_b200_source_run_ids(polycap_source *source, uint64_t see
 	return true;
 }
 
+extern "C" bool polycap_b200_source_sample_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, double *out, polycap_error **error)
+{
+	static const char *W = "polycap_b200_source_sample_ids";
+	if (!check_source(source, error, W))
+		return false;
+	if (!out || n_ids < 0) {
+		polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: out cannot be NULL and n_ids must be >= 0", W);
+		return false;
+	}
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	pcb_gpu_optic *g = optic_for(source->description, source->n_energies, source->energies, NULL, NULL, -1, error, W);
+	if (!g)
+		return false;
+	const pcb_source_desc sd = source_desc(source);
+	if (pcb_gpu_sample_ids(g, &sd, seed, id0, n_ids, out)) {
+		gpu_fail(error, W);
+		return false;
+	}
+	return true;
+}
+
 /* ---- sessions ---- */
 struct _polycap_b200_session {
 	pcb_gpu_optic *g;

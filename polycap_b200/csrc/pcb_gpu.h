@@ -75,6 +75,9 @@ int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, 
 		     double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap, int64_t rec_base,
 		     void *stream, int64_t *ids_used, int64_t *n_exit);
 
+/* start state the tracer draws for ids [id0, id0+n): out[n][11] = coords(3) dir(3) elecv(3) src_x src_y (host memory) */
+int pcb_gpu_sample_ids(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n, double *out_host);
+
 /* dense per-id view of the last wave (debug / parity): status[n] and the 17+nE record of every id */
 int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, double *rec /* [n][17+nE] or NULL */);
 

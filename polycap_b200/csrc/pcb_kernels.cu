@@ -416,6 +416,41 @@ extern "C" int pcb_gpu_replay(pcb_gpu_optic *g, int64_t n, const double *coords,
 	return 0;
 }
 
+/* ------------------------------------------------------------------ start states of ids (parity tooling) */
+
+__global__ void sample_ids_kernel(PcbSource s, int mono, unsigned long long id0, long long n, double *out)
+{
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	StartState st;
+	source_sample(s, mono, id0 + (unsigned long long)i, st);
+	double *o = out + i * 11;
+	o[0] = st.coords.x; o[1] = st.coords.y; o[2] = st.coords.z;
+	o[3] = st.dir.x; o[4] = st.dir.y; o[5] = st.dir.z;
+	o[6] = st.ev.x; o[7] = st.ev.y; o[8] = st.ev.z;
+	o[9] = st.src_x; o[10] = st.src_y;
+}
+
+extern "C" int pcb_gpu_sample_ids(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n, double *out_host)
+{
+	if (n <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	PcbSource ps{};
+	ps.d_source = s->d_source; ps.src_x = s->src_x; ps.src_y = s->src_y; ps.src_sigx = s->src_sigx; ps.src_sigy = s->src_sigy;
+	ps.src_shiftx = s->src_shiftx; ps.src_shifty = s->src_shifty; ps.hor_pol = s->hor_pol;
+	ps.cap0 = g->cap0; ps.ext0 = g->ext0; ps.seed = seed;
+	double *d = nullptr;
+	CK(cudaMalloc(&d, (size_t)n * 11 * 8));
+	sample_ids_kernel<<<(unsigned)((n + 127) / 128), 128>>>(ps, g->o.mono, (unsigned long long)id0, n, d);
+	g->n_kernels++;
+	cudaError_t e = cudaMemcpy(out_host, d, (size_t)n * 11 * 8, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	CK(e);
+	return 0;
+}
+
 /* ------------------------------------------------------------------ wave post-processing */
 
 static const int SCAN_T = 1024;

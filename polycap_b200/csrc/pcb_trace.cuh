@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 	double snx = 0, sny = 0, snz = 0, cosalfa = 0;
 	double dtrav = 0, A = 0, B = 0, inv_dz = 0;
 	int irefl = 0, ix = 0, iseg = 0, ntrace = 0, code = 0;
-	bool slow = false, w_init = false, in_cur = false;
+	bool slow = false, w_init = false, in_cur = false, in_nxt = false;
 	unsigned int c_steps = 0, c_solves = 0, c_refl = 0, c_launch = 0;
 	bool ids_left = true;
 
@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 						if (in_cur && in_next && !slow) {
 							iseg++;
 							c_steps++;
+							in_cur = in_next;
 						} else {
-							st = LS_CAND;
+							st = LS_CAND; /* in_cur keeps describing z[iseg]; in_nxt is adopted when the segment misses */
+							in_nxt = in_next;
 						}
-						in_cur = in_next;
 					}
 				}
 			}
@@ -270,16 +271,18 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 							st = LS_REFL;
 						}
 					} else {
+						/* capil.c:1296-1308: a photon inside the bore of an interior capillary is inside the optic; one that
+						 * left the bore (rejected root, capil.c:134-177) must be tested against the outer hexagon */
 						bool outside = false;
-						if (slow) /* capil.c:1296-1308 */
+						if (slow || !in_cur)
 							outside = (within_pc(T.ext[i], p0.x, p0.y) == 0);
 						if (outside) {
 							code = -1;
 							st = LS_DONE;
 						} else {
 							iseg = i + 1;
+							in_cur = in_nxt;
 							st = LS_SCAN;
-							/* in_cur already describes z[i+1] (set by the scan step that raised CAND) */
 						}
 					}
 				}
@@ -345,7 +348,8 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 					V3 ev = {vx, vy, vz};
 					refl_geometry(sn, d, ev, g);
 					vx = g.new_ev.x; vy = g.new_ev.y; vz = g.new_ev.z;
-					snx = sn.x; sny = sn.y; snz = sn.z;
+					/* snx/sny/snz keep the segment's own normal: capil_reflect renormalises a COPY (capil.c:596), and the
+					 * specular direction below uses capil_trace's un-renormalised one (capil.c:1347-1349) */
 				}
 			}
 			/* energy loop (capil.c:625-645): lanes of the warp read/write consecutive scratch words */

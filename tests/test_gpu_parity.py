@@ -74,26 +74,62 @@ def test_replay_inp_only_configs(pc, name, tmp_path, monkeypatch):
     assert rel_err(out["d_travel"], g["d_travel"]) <= RTOL
 
 
-@pytest.mark.parametrize("name", ["ellip", "parab", "xos1"])
+@pytest.mark.parametrize("name", ["ellip", "parab", "xos1", "conical"])
 def test_source_run_matches_oracle_per_photon(pc, harness, orc, name):
-    """same Philox stream per id on both sides: classification identical, records and tallies to 1e-9"""
+    """Source-driven run, photon by photon.  (1) the start states the device draws from each id's Philox stream agree
+    with the oracle's source sampling over the same stream to rounding (a direct function evaluation: CUDA libm vs
+    glibc differ by a few ulp in tan/atan/acos); (2) the transport is chaotic -- one ulp in a start state grows
+    geometrically over ~40 reflections -- so the trace is checked by feeding the DEVICE's start states to the oracle:
+    classification identical, exit records and tallies to 1e-9."""
     g = load_golden(name)
     desc = _description(pc, g)
     src = _source(pc, g, desc)
     amu, scatf = desc.optical_constants(g["energies"])
     o = harness.Optic(int(g["nmax"]), g["z"], g["cap"], g["ext"], float(g["sig_rough"]), int(g["n_cap"]), float(g["density"]), g["energies"], amu, scatf)
-    n = 6000
-    sw, cnt, status, rec = src.run_ids(4242, 1000, n, records=True)
-    osw, ocnt, ostatus, orec = orc.run_ids(source_of(harness, g), o, 4242, 1000, n, threads=8, records=True)
+    n, seed, id0 = 6000, 4242, 1000
+    starts = src.sample_ids(seed, id0, n)
+    s = source_of(harness, g)
+    worst = 0.0
+    for j in range(0, n, 7):
+        st = harness.OrcPhilox(seed, id0 + j, 0)
+        ph = harness.OrcPhoton()
+        orc.L.orc_source_get_photon(C.byref(s), C.byref(o.c), C.cast(orc.L.orc_philox_uniform, C.c_void_p), C.byref(st), C.byref(ph))
+        want = np.array([*ph.start_coords.t(), *ph.start_direction.t(), *ph.start_electric_vector.t(), ph.src_start_coords.x, ph.src_start_coords.y])
+        scale = np.array([0.2, 0.2, 1, 1e-3, 1e-3, 1, 1, 1, 1e-3, 0.2, 0.2])  # absolute scale of each component
+        worst = max(worst, float(np.max(np.abs(starts[j] - want) / scale)))
+    assert worst < 1e-12, worst
+    sw, cnt, status, rec = src.run_ids(seed, id0, n, records=True)
+    osw, ocnt, ostatus, orec = orc.run_starts(o, starts, threads=8, records=True)
     assert np.array_equal(status, ostatus), np.nonzero(status != ostatus)
     ex = status == 1
-    assert ex.sum() > 100
+    assert ex.sum() > (20 if name == "conical" else 100)
     assert rel_err(rec[ex], orec[ex]) <= RTOL
     assert rel_err(sw, osw) <= RTOL
     assert cnt["exit"] == ocnt["n_exit"] and cnt["not_entered"] == ocnt["n_not_entered"]
     assert cnt["not_transmitted"] == ocnt["n_not_transmitted"] and cnt["uncounted"] == ocnt["n_uncounted"]
     assert cnt["refl_exit"] == ocnt["sum_irefl_exit"] and cnt["refl_all"] == ocnt["sum_irefl_all"]
     assert cnt["ids"] == n
+
+
+def test_source_run_statistics_match_oracle(pc, harness, orc):
+    """north_star check 2: transmission efficiency per energy within 3 sigma binomial error at equal photon counts
+    (independent streams: the oracle samples on the CPU, the device on the GPU, different seeds)"""
+    g = load_golden("ellip")
+    desc = _description(pc, g)
+    src = _source(pc, g, desc)
+    amu, scatf = desc.optical_constants(g["energies"])
+    o = harness.Optic(int(g["nmax"]), g["z"], g["cap"], g["ext"], 0.0, int(g["n_cap"]), float(g["density"]), g["energies"], amu, scatf)
+    n = 40000
+    sw, cnt, _, _ = src.run_ids(1, 0, n, status=False)
+    osw, ocnt, _, _ = orc.run_ids(source_of(harness, g), o, 2, 0, n, threads=8)
+    started = cnt["exit"] + cnt["not_entered"] + cnt["not_transmitted"]
+    ostarted = ocnt["n_exit"] + ocnt["n_not_entered"] + ocnt["n_not_transmitted"]
+    eff, oeff = sw / started, osw / ostarted
+    for e, oe in zip(eff, oeff):
+        sigma = np.sqrt(max(oe * (1 - oe), 1e-6) / started + max(e * (1 - e), 1e-6) / ostarted)
+        assert abs(e - oe) < 3 * sigma, (eff, oeff)
+    p, op = cnt["exit"] / n, ocnt["n_exit"] / n
+    assert abs(p - op) < 3 * np.sqrt(2 * p * (1 - p) / n)
 
 
 def test_exact_checks_mode_agrees(pc, monkeypatch):
