@@ -14,9 +14,6 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#define PCB_COSPI_6 0.86602540378443864676
-#define PCB_PI 3.14159265358979323846
-#define PCB_PI_2 1.57079632679489661923
 
 /* energy-constant rows (one double per energy each) */
 enum { EC_NRE = 0, EC_NIM, EC_I2RE, EC_I2IM, EC_KR, EC_AMU, EC_ROWS };
@@ -45,253 +42,7 @@ struct PcbSource {
 	uint64_t seed;
 };
 
-struct V3 {
-	double x, y, z;
-};
-
-__device__ __forceinline__ double dot3(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; } /* photon.c:379-386 */
-
-__device__ __forceinline__ void norm3(V3 &v) /* photon.c:365-376 */
-{
-	double len = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
-	v.x /= len;
-	v.y /= len;
-	v.z /= len;
-}
-
-/* photon.c:139-169; returns 1 inside, 0 outside, -1 when R <= 0 */
-__device__ __forceinline__ int within_pc(double R, double x, double y)
-{
-	if (R <= 0.)
-		return -1;
-	double apothem = sqrt((R * R) - ((R / 2.) * (R / 2.)));
-	double d1 = fabs(0 * x + 1 * y);
-	double d2 = fabs(PCB_COSPI_6 * x + 0.5 * y);
-	double d3 = fabs(PCB_COSPI_6 * x + -0.5 * y);
-	return (d1 > apothem || d2 > apothem || d3 > apothem) ? 0 : 1;
-}
-
-/* photon.c:540-552 (same code at capil.c:961-973, 1035-1047) */
-__device__ __forceinline__ void hex_cell(double hexz, double x, double y, double &q, double &r)
-{
-	r = y * (2. / 3) / hexz;
-	q = (x / (2. * PCB_COSPI_6) - y / 3) / hexz;
-	double fq = fabs(q - round(q)), fr = fabs(r - round(r)), fs = fabs(-1. * q - r - round(-1. * q - r));
-	if (fq > fr && fq > fs) {
-		q = -1. * round(r) - round(-1. * q - r);
-		r = round(r);
-	} else if (fr > fs) {
-		r = -1. * round(q) - round(-1. * q - r);
-		q = round(q);
-	} else {
-		q = round(q);
-		r = round(r);
-	}
-}
-
-/* ------------------------------------------------------------------ ray / truncated-cone solve
- * capil.c:105-254 (argument checks of :65-100 are done by the callers that can violate them).
- * `last_z` is photon_coord->z on entry.  Returns the reference's code; on 1 fills hit and sn. */
-static __device__ __noinline__ int segment_solve(const V3 &c0, const V3 &c1, double r0, double r1, const V3 &p0, V3 dir, double last_z, V3 &hit, V3 &sn)
-{
-	sn.x = sn.y = sn.z = 0.0;
-	norm3(dir);
-	V3 axis = {c1.x - c0.x, c1.y - c0.y, c1.z - c0.z};
-	double axis_len = sqrt(dot3(axis, axis));
-
-	double ux = (dir.x / dir.z) - (axis.x / axis.z);
-	double uy = (dir.y / dir.z) - (axis.y / axis.z);
-	double sl = (r1 - r0) / (c1.z - c0.z);
-	double a = (ux * ux + uy * uy - sl * sl);
-	double b = (2. * (p0.x - c0.x) * ux + 2. * (p0.y - c0.y) * uy - 2. * r0 * sl);
-	double c = ((p0.x - c0.x) * (p0.x - c0.x) + (p0.y - c0.y) * (p0.y - c0.y) - r0 * r0);
-	double discr = b * b - 4. * a * c;
-	double zi;
-	if (discr < 0)
-		return -2;
-	if (discr == 0) {
-		zi = p0.z + (-1. * b) / (2. * a);
-	} else {
-		double sq = sqrt(discr);
-		double d1 = (-1. * b + sq) / (2. * a);
-		double d2 = (-1. * b - sq) / (2. * a);
-		bool bad1 = (p0.z + d1 < c0.z || p0.z + d1 - last_z < 1.e-5 || p0.z + d1 > c1.z);
-		bool bad2 = (p0.z + d2 < c0.z || p0.z + d2 - last_z < 1.e-5 || p0.z + d2 > c1.z);
-		if (bad1) {
-			if (bad2)
-				return -3;
-			zi = p0.z + d2;
-		} else if (bad2) {
-			zi = p0.z + d1;
-		} else if (p0.z + d2 - last_z < p0.z + d1 - last_z) {
-			zi = p0.z + d2;
-		} else {
-			zi = p0.z + d1;
-		}
-	}
-	if (zi > c1.z)
-		return -4;
-	if (zi < c0.z || zi - last_z < 1.e-5)
-		return -5;
-	double d_proj = (zi - p0.z) / dir.z;
-	if (d_proj < 1.e-10)
-		return -6;
-	hit.x = p0.x + d_proj * dir.x;
-	hit.y = p0.y + d_proj * dir.y;
-	hit.z = zi;
-
-	V3 rel = {p0.x - c0.x, p0.y - c0.y, p0.z - c0.z};
-	double da = dot3(dir, axis);
-	double t = ((d_proj + (dot3(rel, axis) / da)) / (dot3(axis, axis) / da));
-	V3 radial = {hit.x - (c0.x + t * axis.x), hit.y - (c0.y + t * axis.y), hit.z - (c0.z + t * axis.z)};
-	double radial_len = sqrt(dot3(radial, radial));
-	double tga = (r0 - r1) / axis_len;
-	double gam = atan(tga);
-	double sga = sin(gam);
-	double cga = cos(gam);
-	sn.x = cga * radial.x / radial_len + sga * axis.x / axis_len;
-	sn.y = cga * radial.y / radial_len + sga * axis.y / axis_len;
-	sn.z = cga * radial.z / radial_len + sga * axis.z / axis_len;
-	norm3(sn);
-	return 1;
-}
-
-/* ------------------------------------------------------------------ complex helpers
- * The reference evaluates the Fresnel term with C99 complex arithmetic (capil.c:493-511), i.e.
- * with libgcc's __divdc3 and glibc's csqrt/cabs.  These mirror those algorithms for finite,
- * normally scaled operands (third-party code, restated from the published algorithms:
- * libgcc "improved Smith" division; glibc s_csqrt_template.c; glibc e_hypot.c FMA kernel). */
-__device__ __forceinline__ double hypot_g(double x, double y)
-{
-	double ax = fabs(x), ay = fabs(y);
-	if (ax < ay) {
-		double t = ax;
-		ax = ay;
-		ay = t;
-	}
-	if (!(ay > ax * 0x1p-54)) /* also catches ay == 0 and NaN ordering */
-		return ax + ay;
-	double t1 = ay + ay, t2 = ax - ay;
-	if (t1 >= ax)
-		return sqrt(__fma_rn(t1, ax, t2 * t2));
-	return sqrt(__fma_rn(ax, ax, ay * ay));
-}
-
-/* 1.0 / (c + i d)  ==  __divdc3(1.0, 0.0, c, d) */
-__device__ __forceinline__ void cinv_g(double c, double d, double &x, double &y)
-{
-	if (fabs(c) < fabs(d)) {
-		double ratio = c / d;
-		double denom = (c * ratio) + d;
-		x = ((1.0 * ratio) + 0.0) / denom;
-		y = ((0.0 * ratio) - 1.0) / denom;
-	} else {
-		double ratio = d / c;
-		double denom = (d * ratio) + c;
-		x = ((0.0 * ratio) + 1.0) / denom;
-		y = (0.0 - (1.0 * ratio)) / denom;
-	}
-}
-
-__device__ __forceinline__ void csqrt_g(double re, double im, double &r, double &s)
-{
-	if (im == 0.0) {
-		if (re < 0) {
-			r = 0.0;
-			s = copysign(sqrt(-re), im);
-		} else {
-			r = fabs(sqrt(re));
-			s = copysign(0.0, im);
-		}
-		return;
-	}
-	if (re == 0.0) {
-		double h = sqrt(0.5 * fabs(im));
-		r = h;
-		s = copysign(h, im);
-		return;
-	}
-	double d = hypot_g(re, im);
-	if (re > 0) {
-		r = sqrt(0.5 * (d + re));
-		s = 0.5 * (im / r);
-	} else {
-		s = sqrt(0.5 * (d - re));
-		r = fabs(0.5 * (im / s));
-	}
-	s = copysign(s, im);
-}
-
-/* Reflectivity for one energy, capil.c:497-511,538 with the per-energy constants
- * n = 1-alfa+i*beta and (1/n)^2 precomputed on the host in the reference's own order
- * (capil.c:493-495,499).  Keeps the reference's r_p, whose numerator/denominator real parts
- * absorb Im(n cos theta) because of the unparenthesised new_Dcomplex macro (capil.c:35,509). */
-__device__ __forceinline__ double fresnel_rtot(double n_re, double n_im, double i2_re, double i2_im, double cos_t, double sin_t,
-					       double frac_s, double frac_p)
-{
-	double s2 = sin_t * sin_t;
-	double t_re = i2_re * s2, t_im = i2_im * s2;
-	double q_re, q_im;
-	csqrt_g(1.0 - t_re, -1.0 * t_im, q_re, q_im);
-
-	double m_re = n_re * q_re - n_im * q_im; /* n * root */
-	double m_im = n_re * q_im + n_im * q_re;
-	double ix, iy;
-	cinv_g(cos_t + m_re, m_im, ix, iy);
-	double a_re = cos_t - m_re, a_im = -1.0 * m_im;
-	double rs_re = a_re * ix - a_im * iy;
-	double rs_im = a_re * iy + a_im * ix;
-	double rs = hypot_g(rs_re, rs_im);
-	rs *= rs;
-
-	double c_re = n_re * cos_t, c_im = n_im * cos_t; /* n * cos(theta) */
-	cinv_g(q_re + c_re + c_im, q_im, ix, iy);
-	double b_re = q_re - c_re - c_im, b_im = q_im;
-	double rp_re = b_re * ix - b_im * iy;
-	double rp_im = b_re * iy + b_im * ix;
-	double rp = hypot_g(rp_re, rp_im);
-	rp *= rp;
-	return rs * frac_s + rp * frac_p;
-}
-
-/* Energy-independent part of polycap_refl_polar (capil.c:482-490, 497-498, 516-553).
- * `sn` arrives normalised by capil_reflect (capil.c:596); ev is the photon's electric vector
- * (renormalised in place like the reference when its length is not exactly 1). */
-struct ReflGeom {
-	double cos_t, sin_t, frac_s, frac_p;
-	V3 new_ev;
-};
-
-static __device__ __noinline__ void refl_geometry(V3 sn, const V3 &dir, V3 &ev, ReflGeom &g)
-{
-	if (sqrt(sn.x * sn.x + sn.y * sn.y + sn.z * sn.z) != 1)
-		norm3(sn);
-	double theta = acos(dot3(sn, dir));
-	if (sqrt(ev.x * ev.x + ev.y * ev.y + ev.z * ev.z) != 1)
-		norm3(ev);
-	g.cos_t = cos(theta);
-	g.sin_t = sin(theta);
-
-	V3 s, p;
-	s.x = sn.y * dir.z - dir.y * sn.z;
-	s.y = sn.z * dir.x - dir.z * sn.x;
-	s.z = sn.x * dir.y - dir.x * sn.y;
-	norm3(s);
-	p.x = dir.y * s.z - s.y * dir.z;
-	p.y = dir.z * s.x - s.z * dir.x;
-	p.z = dir.x * s.y - s.x * dir.y;
-	norm3(p);
-	double ca = dot3(ev, s);
-	g.frac_s = ca * ca;
-	g.frac_p = 1. - g.frac_s;
-	double cb = dot3(ev, sn);
-	double cc = dot3(ev, p);
-	double fs = g.frac_s, fp = g.frac_p;
-	g.new_ev.x = sqrt((ev.x * ca * fs) * (ev.x * ca * fs) + (ev.x * cb * fp) * (ev.x * cb * fp) + (ev.x * cc * fp) * (ev.x * cc * fp));
-	g.new_ev.y = sqrt((ev.y * ca * fs) * (ev.y * ca * fs) + (ev.y * cb * fp) * (ev.y * cb * fp) + (ev.y * cc * fp) * (ev.y * cc * fp));
-	g.new_ev.z = sqrt((ev.z * ca * fs) * (ev.z * ca * fs) + (ev.z * cb * fp) * (ev.z * cb * fp) + (ev.z * cc * fp) * (ev.z * cc * fp));
-	norm3(g.new_ev);
-}
+#include "pcb_math.h"
 
 /* ------------------------------------------------------------------ Philox4x32-10
  * counter = (id_lo, id_hi, block, 0), key = (seed_lo, seed_hi); draw d of photon `id` is the
