@@ -90,6 +90,10 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 	h = fnv(h, amu.data(), nE * 8);
 	h = fnv(h, scatf.data(), nE * 8);
 	h = fnv(h, &device, sizeof device);
+	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS"}) { /* modes read at optic creation */
+		const char *v = getenv(k);
+		h = fnv(h, v ? v : "", v ? strlen(v) + 1 : 1);
+	}
 	CachedOptic *slot = &g_cache[0];
 	const bool no_cache = getenv("POLYCAP_B200_NO_CACHE") != NULL; /* re-upload the tables on every call (end-to-end timing) */
 	for (auto &c : g_cache) {

@@ -66,6 +66,7 @@ struct pcb_gpu_optic {
 	int threads = 256, ctas_per_sm = 2;
 	int thr_cand = 12, thr_refl = 12, thr_new = 8;
 	int tables_in_smem = 1;
+	int exact_weights = 0;
 	double cap0 = 0, ext0 = 0;
 	/* wave buffers (grown on demand) */
 	int64_t wave_cap = 0;
@@ -150,12 +151,17 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 		hhex[i] = d->ext[i] / (2. * COSPI_6_HOST * (n_shells + 1));
 		hrm[i] = d->cap[i] * d->cap[i] * (1.0 - eps);
 		double apo = sqrt((d->ext[i] * d->ext[i]) - ((d->ext[i] / 2.) * (d->ext[i] / 2.)));
-		double room = (apo * (1.0 - eps) - d->cap[i]) / hhex[i];
+		/* interior capillary: bore wall plus the largest lateral excursion of a back-extrapolated restart point
+		 * (one segment length at tan(theta) <= 0.25, see trace_begin) stays inside the outer hexagon at every z */
+		double dzmax = 0;
+		if (i > 0) dzmax = fmax(dzmax, d->z[i] - d->z[i - 1]);
+		if (i + 1 < n) dzmax = fmax(dzmax, d->z[i + 1] - d->z[i]);
+		double room = (apo * (1.0 - eps) - d->cap[i] - 0.25 * dzmax) / hhex[i];
 		if (!(room < 1e300))
 			room = -1;
 		if (room < m_safe)
 			m_safe = room;
-		if (!(d->cap[i] < apo * (1.0 - eps) && d->cap[i] < d->ext[i] * (1.0 - eps) && d->cap[i] * d->cap[i] < d->ext[i] * (1.0 - eps)))
+		if (!(d->cap[i] + 0.25 * dzmax < apo * (1.0 - eps) && d->cap[i] < d->ext[i] * (1.0 - eps) && d->cap[i] * d->cap[i] < d->ext[i] * (1.0 - eps)))
 			mono_ok = false;
 		if (!(d->cap[i] > 0) || !(d->ext[i] > 0))
 			m_safe = -1;
@@ -205,6 +211,7 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	if ((e = getenv("POLYCAP_B200_THR_REFL"))) g->thr_refl = atoi(e);
 	if ((e = getenv("POLYCAP_B200_THR_NEW"))) g->thr_new = atoi(e);
 	if ((e = getenv("POLYCAP_B200_CTAS_PER_SM"))) g->ctas_per_sm = atoi(e);
+	if ((e = getenv("POLYCAP_B200_EXACT_FRESNEL"))) g->exact_weights = atoi(e);
 	return g;
 }
 
@@ -350,13 +357,18 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 	}
 	g->n_kernels++;
 	g->n_trace++;
+	/* EXACT_W = 1: per-energy Fresnel term in the reference's operation order (bit-level weights); 0: the cheap evaluation */
+#define PCB_LAUNCH(M, X)                                                                                                  \
+	do {                                                                                                              \
+		CK(cudaFuncSetAttribute(pcb_trace_kernel<M, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		pcb_trace_kernel<M, X><<<blocks, g->threads, smem, stream>>>(P);                                          \
+	} while (0)
 	if (mode == MODE_SOURCE) {
-		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_SOURCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		pcb_trace_kernel<MODE_SOURCE><<<blocks, g->threads, smem, stream>>>(P);
+		if (g->exact_weights) PCB_LAUNCH(MODE_SOURCE, 1); else PCB_LAUNCH(MODE_SOURCE, 0);
 	} else {
-		CK(cudaFuncSetAttribute(pcb_trace_kernel<MODE_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		pcb_trace_kernel<MODE_REPLAY><<<blocks, g->threads, smem, stream>>>(P);
+		if (g->exact_weights) PCB_LAUNCH(MODE_REPLAY, 1); else PCB_LAUNCH(MODE_REPLAY, 0);
 	}
+#undef PCB_LAUNCH
 	if (g->timing) {
 		cudaEventRecord(e1, stream);
 		g->ev_pending.emplace_back(e0, e1);

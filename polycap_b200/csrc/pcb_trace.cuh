@@ -59,7 +59,7 @@ struct PcbTraceParams {
 	PcbReplayIn rin;
 	PcbWaveOut out;
 	PcbWorkCounters *wc;
-	double *wscratch;          /* [nE][total_threads] */
+	double *wscratch;          /* [total_threads][nE]: one weight vector per persistent lane */
 	unsigned long long id0;    /* global id of local index 0 */
 	unsigned long long n_ids;
 	int mode;
@@ -83,7 +83,7 @@ struct Tables {
 	const double *z, *cap, *ext, *hexz, *rm;
 };
 
-template <int MODE>
+template <int MODE, int EXACT_W>
 __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 	const int nE = o.n_energies;
 	const int lane = threadIdx.x & 31;
 	const unsigned long long slot = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned long long n_slots = (unsigned long long)gridDim.x * blockDim.x;
 
 	/* ---- stage the five profile tables in shared memory ------------------------------- */
 	Tables T;
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 	}
 
 	const double *ec = o.ec;
-	double *wsl = P.wscratch + slot; /* element e at wsl[e * n_slots] */
+	double *wsl = P.wscratch + slot * (unsigned long long)nE; /* this lane's weight vector: element e at wsl[e] */
 
 	/* ---- per-lane photon state ---------------------------------------------------------- */
 	int st = LS_NEW;
@@ -145,8 +144,9 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 	unsigned int c_steps = 0, c_solves = 0, c_refl = 0, c_launch = 0;
 	bool ids_left = true;
 
-	/* begin one capil_trace call (capil.c:1236-1246): renormalise, reset photon_coord */
-	auto trace_begin = [&]() {
+	/* begin one capil_trace call (capil.c:1236-1246): renormalise, reset photon_coord.
+	 * on_wall: the call follows a reflection, i.e. the photon sits ON the bore wall inside segment ix and heads inwards. */
+	auto trace_begin = [&](bool on_wall) {
 		if (ntrace > nmax) { /* launch loop ran nmax+1 times with iesc==1 (photon.c:912-919) */
 			code = 1;
 			st = LS_DONE;
@@ -159,13 +159,23 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 		lhx = ex; lhy = ey; lhz = ez;
 		iseg = ix;
 		inv_dz = 1.0 / dz;
-		/* is the (back-)extrapolated photon clearly inside the bore at z[iseg]? */
 		if (iseg < nmax) {
-			double t = (T.z[iseg] - ez) * inv_dz;
-			double hz = T.hexz[iseg];
-			double ux = __fma_rn(-A, hz, __fma_rn(dx, t, ex));
-			double uy = __fma_rn(-B, hz, __fma_rn(dy, t, ey));
-			in_cur = __fma_rn(ux, ux, uy * uy) < T.rm[iseg];
+			/* "No wall hit possible in segment iseg" needs the photon inside the bore at both ends (convexity).
+			 * Restarting on the wall the same holds from the hit point on: distance-to-axis minus radius is convex in z,
+			 * zero at the hit and negative at z[iseg+1], and the root at the hit itself is rejected by the reference's
+			 * 1e-5 forward margin (capil.c:134-156).  The back-extrapolated point at z[iseg], which the reference tests
+			 * against the outer hexagon (capil.c:1296-1308), lies at most dz*tan(theta) beyond the wall: inside the
+			 * hexagon for interior capillaries (m_safe carries that margin) unless the photon is steep. */
+			const bool steep = (dx * dx + dy * dy) > 0.0625 * (dz * dz);
+			if (on_wall && !steep) {
+				in_cur = true;
+			} else {
+				double t = (T.z[iseg] - ez) * inv_dz;
+				double hz = T.hexz[iseg];
+				double ux = pcb_fma(-A, hz, pcb_fma(dx, t, ex));
+				double uy = pcb_fma(-B, hz, pcb_fma(dy, t, ey));
+				in_cur = pcb_fma(ux, ux, uy * uy) < T.rm[iseg];
+			}
 		}
 		st = LS_SCAN;
 	};
@@ -202,9 +212,9 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 					} else {
 						double t = (T.z[iseg + 1] - ez) * inv_dz;
 						double hz = T.hexz[iseg + 1];
-						double ux = __fma_rn(-A, hz, __fma_rn(dx, t, ex));
-						double uy = __fma_rn(-B, hz, __fma_rn(dy, t, ey));
-						bool in_next = __fma_rn(ux, ux, uy * uy) < T.rm[iseg + 1];
+						double ux = pcb_fma(-A, hz, pcb_fma(dx, t, ex));
+						double uy = pcb_fma(-B, hz, pcb_fma(dy, t, ey));
+						bool in_next = pcb_fma(ux, ux, uy * uy) < T.rm[iseg + 1];
 						if (in_cur && in_next && !slow) {
 							iseg++;
 							c_steps++;
@@ -352,32 +362,67 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 					 * specular direction below uses capil_trace's un-renormalised one (capil.c:1347-1349) */
 				}
 			}
-			/* energy loop (capil.c:625-645): lanes of the warp read/write consecutive scratch words */
-			if (mine) {
+			/* energy loop (capil.c:625-645), spread over ALL lanes of the warp: the (photon, energy) pairs of the lanes that
+			 * reflect in this round are dealt out 32 at a time, so the per-energy Fresnel term -- the bulk of the work at
+			 * large nE -- runs fully converged however few photons reflect together.  Geometry travels by shuffle, the
+			 * weight vectors sit photon-major in the warp's scratch slab (consecutive pairs -> consecutive words). */
+			{
+				const unsigned go = __ballot_sync(0xffffffffu, mine);
+				const int n_go = __popc(go);
+				const int total = n_go * nE;
 				const bool rough = (o.sig_rough != 0.0);
-				for (int e = 0; e < nE; e++) {
-					double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
-					double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
-					double rtot = fresnel_rtot(n_re, n_im, i2_re, i2_im, g.cos_t, g.sin_t, g.frac_s, g.frac_p);
-					double w = w_init ? wsl[(unsigned long long)e * n_slots] : 1.0;
-					if (rough) {
-						double cons1 = __ldg(ec + EC_KR * nE + e) * alfa * o.sig_rough;
-						double r_rough = exp(-1. * cons1 * cons1);
-						w = w * rtot * r_rough;
-					} else {
-						w = w * rtot * 1.0;
+				const double sig_rough = o.sig_rough;
+				unsigned alive_bits = 0, bad_bits = 0;
+				double *wwarp = P.wscratch + (slot - lane) * (unsigned long long)nE;
+				int pi = lane / nE, e = lane - pi * nE; /* pair index -> (rank of photon among `go`, energy) */
+				const int dpi = 32 / nE, de = 32 - dpi * nE;
+				for (int j0 = 0; j0 < total; j0 += 32) {
+					const bool valid = (j0 + lane) < total;
+					const int src = valid ? (int)__fns(go, 0, pi + 1) : lane;
+					const double cos_t = __shfl_sync(0xffffffffu, g.cos_t, src);
+					const double sin_t = __shfl_sync(0xffffffffu, g.sin_t, src);
+					const double frac_s = __shfl_sync(0xffffffffu, g.frac_s, src);
+					const double frac_p = __shfl_sync(0xffffffffu, g.frac_p, src);
+					const double alfa_s = __shfl_sync(0xffffffffu, alfa, src);
+					const int winit_s = __shfl_sync(0xffffffffu, (int)w_init, src);
+					if (valid) {
+						const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
+						const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
+						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, cos_t, sin_t, frac_s, frac_p)
+									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, cos_t, sin_t, frac_s, frac_p);
+						double *wp = wwarp + (unsigned long long)src * nE + e;
+						double w = winit_s ? *wp : 1.0;
+						if (rough) {
+							const double cons1 = __ldg(ec + EC_KR * nE + e) * alfa_s * sig_rough;
+							const double r_rough = exp(-1. * cons1 * cons1);
+							w = w * rtot * r_rough;
+						} else {
+							w = w * rtot * 1.0;
+						}
+						*wp = w;
+						if (rtot < 0. || rtot > 1.) /* capil.c:632-636 */
+							bad_bits |= 1u << src;
+						if (w >= 1.e-4)
+							alive_bits |= 1u << src;
 					}
-					wsl[(unsigned long long)e * n_slots] = w;
-					if (rtot < 0. || rtot > 1.) { /* capil.c:632-636 */
+					pi += dpi;
+					e += de;
+					if (e >= nE) {
+						e -= nE;
+						pi++;
+					}
+				}
+				alive_bits = __reduce_or_sync(0xffffffffu, alive_bits);
+				bad_bits = __reduce_or_sync(0xffffffffu, bad_bits);
+				if (mine) {
+					w_init = true;
+					alive = (alive_bits >> lane) & 1u;
+					if ((bad_bits >> lane) & 1u) {
 						code = -1;
 						st = LS_DONE;
 						mine = false;
-						break;
 					}
-					if (w >= 1.e-4)
-						alive = true;
 				}
-				w_init = true;
 			}
 			if (mine) {
 				if (alive) { /* capil.c:1346-1352 */
@@ -388,7 +433,7 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 					norm3(d);
 					dx = d.x; dy = d.y; dz = d.z;
 					irefl++;
-					trace_begin();
+					trace_begin(true);
 				} else {
 					code = 0;
 					st = LS_DONE;
@@ -456,7 +501,7 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 				if (wr_rec || status == ST_ABSORBED) {
 					double *W = P.out.weights + lid * (unsigned long long)nE;
 					for (int e = 0; e < nE; e++)
-						W[e] = w_init ? wsl[(unsigned long long)e * n_slots] : 1.0;
+						W[e] = w_init ? wsl[e] : 1.0;
 				}
 				st = LS_NEW;
 			}
@@ -556,7 +601,7 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 						double m1 = fabs(B), m2 = fabs(PCB_COSPI_6 * A + 0.5 * B), m3 = fabs(PCB_COSPI_6 * A - 0.5 * B);
 						double mm = fmax(m1, fmax(m2, m3));
 						slow = o.all_slow || !(mm < o.m_safe);
-						trace_begin();
+						trace_begin(false);
 					}
 				}
 			}

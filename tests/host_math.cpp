@@ -70,6 +70,12 @@ double hm_refl(const double sn[3], const double dir[3], double ev[3], const doub
 	new_ev[0] = g.new_ev.x; new_ev[1] = g.new_ev.y; new_ev[2] = g.new_ev.z;
 	return fresnel_rtot(ec[0], ec[1], ec[2], ec[3], g.cos_t, g.sin_t, g.frac_s, g.frac_p);
 }
+// fast vs reference-order Fresnel term on the same (bit-identical) geometry; returns both
+void hm_fresnel_pair(const double ec[4], double cos_t, double sin_t, double frac_s, double out[2])
+{
+	out[0] = fresnel_rtot(ec[0], ec[1], ec[2], ec[3], cos_t, sin_t, frac_s, 1. - frac_s);
+	out[1] = fresnel_rtot_fast(ec[0], ec[1], ec[2], ec[3], cos_t, sin_t, frac_s, 1. - frac_s);
+}
 int hm_segment(const double in[20], double out[6])
 {
 	V3 c0 = {in[0], in[1], in[2]}, c1 = {in[3], in[4], in[5]}, p0 = {in[8], in[9], in[10]}, dir = {in[14], in[15], in[16]}, hit = {in[17], in[18], in[19]}, sn;
