@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ __align__(8) uint64_t tma_bar;
+	enum { STG_N = 6 };
+	__shared__ double stage[8 * 32 * STG_N]; /* per-warp strip: cos, sin, frac_s, frac_p, alfa, (w_init, lane) of reflecting photons */
 
 	const PcbOptic &o = P.o;
 	const int nmax = o.nmax;
@@ -356,7 +358,10 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 					mine = false;
 				} else {
 					V3 ev = {vx, vy, vz};
-					refl_geometry(sn, d, ev, g);
+					if (EXACT_W)
+						refl_geometry(sn, d, ev, g);
+					else
+						refl_geometry_fast(sn, d, ev, g);
 					vx = g.new_ev.x; vy = g.new_ev.y; vz = g.new_ev.z;
 					/* snx/sny/snz keep the segment's own normal: capil_reflect renormalises a COPY (capil.c:596), and the
 					 * specular direction below uses capil_trace's un-renormalised one (capil.c:1347-1349) */
@@ -374,42 +379,65 @@ __global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams 
 				const double sig_rough = o.sig_rough;
 				unsigned alive_bits = 0, bad_bits = 0;
 				double *wwarp = P.wscratch + (slot - lane) * (unsigned long long)nE;
+				/* stage the reflecting photons' geometry, rank-ordered, in this warp's shared-memory strip */
+				double *stg = stage + (threadIdx.x >> 5) * (32 * STG_N);
+				if (mine) {
+					double *q = stg + __popc(go & ((1u << lane) - 1u)) * STG_N;
+					q[0] = g.cos_t; q[1] = g.sin_t; q[2] = g.frac_s; q[3] = g.frac_p; q[4] = alfa;
+					q[5] = __hiloint2double(w_init ? 1 : 0, lane);
+				}
+				__syncwarp();
 				int pi = lane / nE, e = lane - pi * nE; /* pair index -> (rank of photon among `go`, energy) */
 				const int dpi = 32 / nE, de = 32 - dpi * nE;
+				/* software pipeline: the weight of the next pair is loaded while the current one is evaluated */
+				bool valid = lane < total;
+				int src = 0, winit = 0;
+				double w_next = 1.0;
+				if (valid) {
+					const double tag = stg[pi * STG_N + 5];
+					src = __double2loint(tag);
+					winit = __double2hiint(tag);
+					if (winit)
+						w_next = wwarp[(unsigned long long)src * nE + e];
+				}
 				for (int j0 = 0; j0 < total; j0 += 32) {
-					const bool valid = (j0 + lane) < total;
-					const int src = valid ? (int)__fns(go, 0, pi + 1) : lane;
-					const double cos_t = __shfl_sync(0xffffffffu, g.cos_t, src);
-					const double sin_t = __shfl_sync(0xffffffffu, g.sin_t, src);
-					const double frac_s = __shfl_sync(0xffffffffu, g.frac_s, src);
-					const double frac_p = __shfl_sync(0xffffffffu, g.frac_p, src);
-					const double alfa_s = __shfl_sync(0xffffffffu, alfa, src);
-					const int winit_s = __shfl_sync(0xffffffffu, (int)w_init, src);
-					if (valid) {
-						const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
-						const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
-						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, cos_t, sin_t, frac_s, frac_p)
-									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, cos_t, sin_t, frac_s, frac_p);
-						double *wp = wwarp + (unsigned long long)src * nE + e;
-						double w = winit_s ? *wp : 1.0;
-						if (rough) {
-							const double cons1 = __ldg(ec + EC_KR * nE + e) * alfa_s * sig_rough;
-							const double r_rough = exp(-1. * cons1 * cons1);
-							w = w * rtot * r_rough;
-						} else {
-							w = w * rtot * 1.0;
-						}
-						*wp = w;
-						if (rtot < 0. || rtot > 1.) /* capil.c:632-636 */
-							bad_bits |= 1u << src;
-						if (w >= 1.e-4)
-							alive_bits |= 1u << src;
-					}
+					const bool v_cur = valid;
+					const int src_cur = src, e_cur = e, pi_cur = pi;
+					double w = w_next;
+					/* advance to the next pair and issue its load */
 					pi += dpi;
 					e += de;
 					if (e >= nE) {
 						e -= nE;
 						pi++;
+					}
+					valid = (j0 + 32 + lane) < total;
+					w_next = 1.0;
+					if (valid) {
+						const double tag = stg[pi * STG_N + 5];
+						src = __double2loint(tag);
+						winit = __double2hiint(tag);
+						if (winit)
+							w_next = wwarp[(unsigned long long)src * nE + e];
+					}
+					if (v_cur) {
+						const double *q = stg + pi_cur * STG_N;
+						const double n_re = __ldg(ec + EC_NRE * nE + e_cur), n_im = __ldg(ec + EC_NIM * nE + e_cur);
+						const double i2_re = __ldg(ec + EC_I2RE * nE + e_cur), i2_im = __ldg(ec + EC_I2IM * nE + e_cur);
+						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, q[0], q[1], q[2], q[3])
+									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, q[0], q[1], q[2], q[3]);
+						if (rough) {
+							const double cons1 = __ldg(ec + EC_KR * nE + e_cur) * q[4] * sig_rough;
+							const double r_rough = exp(-1. * cons1 * cons1);
+							w = w * rtot * r_rough;
+						} else {
+							w = w * rtot * 1.0;
+						}
+						wwarp[(unsigned long long)src_cur * nE + e_cur] = w;
+						if (rtot < 0. || rtot > 1.) /* capil.c:632-636 */
+							bad_bits |= 1u << src_cur;
+						if (w >= 1.e-4)
+							alive_bits |= 1u << src_cur;
 					}
 				}
 				alive_bits = __reduce_or_sync(0xffffffffu, alive_bits);

@@ -44,7 +44,7 @@ def test_replay_matches_reference_corpus(pc, name, exact, monkeypatch):
     assert rel_err(out["exit_coords"], g["exit_state"][:, 0:3]) == 0.0
     assert rel_err(out["exit_direction"], g["exit_state"][:, 3:6]) == 0.0
     assert rel_err(out["d_travel"], g["d_travel"]) == 0.0
-    assert rel_err(out["exit_electric_vector"], g["exit_state"][:, 6:9]) <= 1e-13
+    assert rel_err(out["exit_electric_vector"], g["exit_state"][:, 6:9]) <= (1e-13 if exact else RTOL)
     traced = np.isin(g["ret"], (0, 1))
     assert rel_err(out["weights"][traced], g["weights"][traced]) <= (1e-13 if exact else RTOL)
 
