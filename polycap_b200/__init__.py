@@ -20,7 +20,7 @@ import numpy as np
 __version__ = "1.2"
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolycap_b200.so")
+LIB_PATH = os.environ.get("POLYCAP_B200_LIB") or os.path.join(_HERE, "libpolycap_b200.so")  # env override: kernel-variant experiments
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -63,7 +63,7 @@ struct pcb_gpu_optic {
 	double *d_wscratch = nullptr;
 	PcbWorkCounters *d_wc = nullptr;
 	size_t table_bytes = 0; /* tb */
-	int threads = 256, ctas_per_sm = 2;
+	int threads = PCB_LB_THREADS, ctas_per_sm = PCB_LB_CTAS;
 	int thr_cand = 12, thr_refl = 12, thr_new = 8;
 	int tables_in_smem = 1;
 	int exact_weights = 0;

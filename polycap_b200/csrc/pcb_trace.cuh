@@ -84,12 +84,16 @@ struct Tables {
 };
 
 template <int MODE, int EXACT_W>
-__global__ void __launch_bounds__(256, 2) pcb_trace_kernel(const PcbTraceParams P)
+#ifndef PCB_LB_THREADS
+#define PCB_LB_THREADS 256
+#define PCB_LB_CTAS 2
+#endif
+__global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(const PcbTraceParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ __align__(8) uint64_t tma_bar;
 	enum { STG_N = 6 };
-	__shared__ double stage[8 * 32 * STG_N]; /* per-warp strip: cos, sin, frac_s, frac_p, alfa, (w_init, lane) of reflecting photons */
+	__shared__ double stage[(PCB_LB_THREADS / 32) * 32 * STG_N]; /* per-warp strip: cos, sin, frac_s, frac_p, alfa, (w_init, lane) of reflecting photons */
 
 	const PcbOptic &o = P.o;
 	const int nmax = o.nmax;
