@@ -56,6 +56,17 @@ POLYCAP_EXTERN bool polycap_b200_photon_launch_batch(polycap_description *descri
 						     double *exit_coords, double *exit_direction, double *exit_electric_vector, int64_t *i_refl,
 						     double *d_travel, double *weights, int64_t *counters, polycap_error **error);
 
+/* The same with leak_calc = true (leak / recap wall transport, src/polycap-capil.c:896-1194, 658-887).  leak_count[n][2] receives
+ * the number of external and internal leak records of each photon; *leak_records is malloc'd (free with polycap_free) and holds
+ * *n_leak_records records of 11 + n_energies doubles in photon order: kind (0 external, 1 internal), coords(3), direction(3),
+ * electric vector(3), n_refl, weights(n_energies) -- the fields of polycap_leak (include/polycap-photon.h:52-59). */
+POLYCAP_EXTERN bool polycap_b200_photon_launch_batch_leaks(polycap_description *description, size_t n_energies, const double *energies,
+							   const double *amu, const double *scatf, int64_t n, const double *start_coords,
+							   const double *start_direction, const double *start_electric_vector, int *ret, double *exit_coords,
+							   double *exit_direction, double *exit_electric_vector, int64_t *i_refl, double *d_travel,
+							   double *weights, int64_t *leak_count, double **leak_records, int64_t *n_leak_records,
+							   polycap_error **error);
+
 /* Source-driven run over photon ids [id0, id0+n_ids) with seed `seed`, results on the host:
  * sum_weights[nE] (exit photons only), counters[POLYCAP_B200_N_COUNTERS], optional status[n_ids]
  * (1 exit, 0 absorbed, 2 not entered, -2/-1, 3 = reached the end outside the exit window) and optional

@@ -109,6 +109,10 @@ _optical_constants = _sig("polycap_b200_optical_constants", C.c_bool, [_v, C.c_s
 _launch_batch = _sig("polycap_b200_photon_launch_batch", C.c_bool,
                      [_v, C.c_size_t, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, C.c_bool,
                       C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_int64_p, _ErrPP])
+_launch_batch_leaks = _sig("polycap_b200_photon_launch_batch_leaks", C.c_bool,
+                           [_v, C.c_size_t, c_double_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p,
+                            C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p, c_double_p, c_int64_p,
+                            C.POINTER(c_double_p), c_int64_p, _ErrPP])
 _run_ids = _sig("polycap_b200_source_run_ids", C.c_bool,
                 [_v, C.c_uint64, C.c_int64, C.c_int64, C.c_bool, c_double_p, c_int64_p, C.POINTER(C.c_int8), c_double_p, _ErrPP])
 _sample_ids = _sig("polycap_b200_source_sample_ids", C.c_bool, [_v, C.c_uint64, C.c_int64, C.c_int64, c_double_p, _ErrPP])
@@ -586,8 +590,9 @@ class Source:
         return sw, dict(zip(COUNTER_NAMES, cnt.tolist())), st, rec
 
 
-def launch_batch(description, energies, start_coords, start_direction, start_electric_vector, amu=None, scatf=None):
-    """Batched polycap_photon_launch: returns dict(ret, exit_coords, exit_direction, exit_electric_vector, i_refl, d_travel, weights, counters)"""
+def launch_batch(description, energies, start_coords, start_direction, start_electric_vector, amu=None, scatf=None, leak_calc=False):
+    """Batched polycap_photon_launch: returns dict(ret, exit_coords, exit_direction, exit_electric_vector, i_refl, d_travel, weights, counters);
+    with leak_calc=True additionally leaks = per-photon dict(ext=[...], int=[...]) of dict(coords, direction, elecv, n_refl, weight)."""
     en = np.ascontiguousarray(np.atleast_1d(energies), dtype=np.double)
     c = np.ascontiguousarray(start_coords, dtype=np.double).reshape(-1, 3)
     d = np.ascontiguousarray(start_direction, dtype=np.double).reshape(-1, 3)
@@ -604,12 +609,34 @@ def launch_batch(description, energies, start_coords, start_direction, start_ele
     w = np.zeros((n, en.size))
     cnt = np.zeros(N_COUNTERS, dtype=np.int64)
     e = _err()
-    _launch_batch(description._description, en.size, _dp(en), _dp(a) if a is not None else None, _dp(s) if s is not None else None, n,
-                  _dp(c), _dp(d), _dp(v), False, ret.ctypes.data_as(C.POINTER(C.c_int)), _dp(ec), _dp(ed), _dp(ev),
-                  ir.ctypes.data_as(c_int64_p), _dp(dt), _dp(w), cnt.ctypes.data_as(c_int64_p), C.byref(e))
+    common = [description._description, en.size, _dp(en), _dp(a) if a is not None else None, _dp(s) if s is not None else None, n, _dp(c), _dp(d), _dp(v)]
+    outs = [ret.ctypes.data_as(C.POINTER(C.c_int)), _dp(ec), _dp(ed), _dp(ev), ir.ctypes.data_as(c_int64_p), _dp(dt), _dp(w)]
+    out = dict(ret=ret, exit_coords=ec, exit_direction=ed, exit_electric_vector=ev, i_refl=ir, d_travel=dt, weights=w)
+    if not leak_calc:
+        _launch_batch(*common, False, *outs, cnt.ctypes.data_as(c_int64_p), C.byref(e))
+        _raise(e)
+        out["counters"] = dict(zip(COUNTER_NAMES, cnt.tolist()))
+        return out
+    lcount = np.zeros((n, 2), dtype=np.int64)
+    recs, nrec = c_double_p(), C.c_int64(0)
+    _launch_batch_leaks(*common, *outs, lcount.ctypes.data_as(c_int64_p), C.byref(recs), C.byref(nrec), C.byref(e))
     _raise(e)
-    return dict(ret=ret, exit_coords=ec, exit_direction=ed, exit_electric_vector=ev, i_refl=ir, d_travel=dt, weights=w,
-                counters=dict(zip(COUNTER_NAMES, cnt.tolist())))
+    stride = 11 + en.size
+    R = np.ctypeslib.as_array(recs, (nrec.value, stride)).copy() if nrec.value else np.zeros((0, stride))
+    if recs:
+        _free(recs)
+    leaks, k = [], 0
+    for i in range(n):
+        m = int(lcount[i].sum())
+        per = {"ext": [], "int": []}
+        for r in R[k:k + m]:
+            per["ext" if r[0] == 0 else "int"].append(dict(coords=r[1:4].copy(), direction=r[4:7].copy(), elecv=r[7:10].copy(), n_refl=int(r[10]),
+                                                            weight=r[11:].copy()))
+        leaks.append(per)
+        k += m
+    out["leaks"] = leaks
+    out["leak_count"] = lcount
+    return out
 
 
 class Session:

@@ -325,10 +325,6 @@ struct ReplayOut {
 	std::vector<int64_t> irefl;
 };
 
-extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state,
-				   int64_t *irefl, double *weights, int64_t *counters, int64_t *leak_count /* [n][2] */, double **leak_rec,
-				   int64_t *n_leak_rec);
-
 /* photon.c:390-955 */
 extern "C" int polycap_photon_launch(polycap_photon *photon, size_t n_energies, double *energies, double **weights, bool leak_calc,
 				     polycap_error **error)
@@ -542,10 +538,6 @@ static pcb_source_desc source_desc(const polycap_source *s)
 }
 
 extern "C" void polycap_transmission_efficiencies_free(polycap_transmission_efficiencies *efficiencies);
-
-extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
-				     double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap,
-				     int64_t rec_base, int64_t *ids_used, int64_t *n_exit, double **leak_rec, int64_t *n_leak_rec);
 
 extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_efficiencies(polycap_source *source, int max_threads, int n_photons,
 											    bool leak_calc, polycap_progress_monitor *progress_monitor,
@@ -1003,14 +995,6 @@ extern "C" double polycap_refl_polar(double e, double density, double scatf, dou
 	return out[0];
 }
 
-extern "C" int pcb_unit_reflect_leak(const double in[13], const double *z, const double *cap, const double *ext, int nmax, int64_t n_cap, const double *ec,
-				     int nE, double sig_rough, double *w, double out[6], int64_t *leak_count, double **leak_rec, int64_t *n_leak_rec);
-extern "C" int pcb_unit_trace_leak(const double in[10], int *ix, long long *irefl, const double *z, const double *cap, const double *ext, const double *cap_x,
-				   const double *cap_y, int nmax, int64_t n_cap, const double *ec, int nE, double sig_rough, double *w, double out[10],
-				   int64_t *leak_count, double **leak_rec, int64_t *n_leak_rec);
-extern "C" int pcb_unit_trace_wall(const double in[6], const double *z, const double *cap, const double *ext, int nmax, int64_t n_cap, double *d_travel,
-				   int *r_cntr, int *q_cntr);
-
 static void append_leaks(polycap_photon *photon, size_t nE, const double *lrec, int64_t n_rec)
 {
 	const size_t stride = 11 + nE;
@@ -1047,23 +1031,13 @@ extern "C" int polycap_capil_reflect(polycap_photon *photon, polycap_vector3 sur
 	energy_constants_for(photon, d, ec);
 	double out[6];
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
-	int rc;
-	if (leak_calc) {
-		const double in[13] = {photon->exit_direction.x, photon->exit_direction.y, photon->exit_direction.z, photon->exit_electric_vector.x,
-				       photon->exit_electric_vector.y, photon->exit_electric_vector.z, surface_norm.x, surface_norm.y, surface_norm.z,
-				       photon->exit_coords.x, photon->exit_coords.y, photon->exit_coords.z, (double)photon->i_refl};
-		int64_t lcount[2] = {0, 0}, n_rec = 0;
-		double *lrec = NULL;
-		rc = pcb_unit_reflect_leak(in, d->profile->z, d->profile->cap, d->profile->ext, d->profile->nmax, d->n_cap, ec.data(), (int)photon->n_energies,
-					   d->sig_rough, photon->weight, out, lcount, &lrec, &n_rec);
-		if (rc > -100)
-			append_leaks(photon, photon->n_energies, lrec, n_rec);
-		free(lrec);
-	} else {
-		const double in[9] = {photon->exit_direction.x, photon->exit_direction.y, photon->exit_direction.z, photon->exit_electric_vector.x,
-				      photon->exit_electric_vector.y, photon->exit_electric_vector.z, surface_norm.x, surface_norm.y, surface_norm.z};
-		rc = pcb_unit_reflect(in, ec.data(), (int)photon->n_energies, d->sig_rough, photon->weight, out);
+	if (leak_calc) { /* the leak state machine runs whole photons (pcb_leak.cu); its single-step form is not exposed */
+		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc=true is served by polycap_photon_launch / polycap_source_get_transmission_efficiencies", W);
+		return -1;
 	}
+	const double in[9] = {photon->exit_direction.x, photon->exit_direction.y, photon->exit_direction.z, photon->exit_electric_vector.x,
+			      photon->exit_electric_vector.y, photon->exit_electric_vector.z, surface_norm.x, surface_norm.y, surface_norm.z};
+	int rc = pcb_unit_reflect(in, ec.data(), (int)photon->n_energies, d->sig_rough, photon->weight, out);
 	if (unit_failed(rc, error, W))
 		return -1;
 	photon->exit_direction.x = out[0]; photon->exit_direction.y = out[1]; photon->exit_direction.z = out[2];
@@ -1101,19 +1075,12 @@ extern "C" int polycap_capil_trace(int *ix, polycap_photon *photon, polycap_desc
 	double out[10];
 	long long irefl = photon->i_refl;
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
-	int rc;
 	if (leak_calc) {
-		int64_t lcount[2] = {0, 0}, n_rec = 0;
-		double *lrec = NULL;
-		rc = pcb_unit_trace_leak(in, ix, &irefl, p->z, p->cap, p->ext, cap_x, cap_y, p->nmax, description->n_cap, ec.data(), (int)photon->n_energies,
-					 description->sig_rough, photon->weight, out, lcount, &lrec, &n_rec);
-		if (rc > -100)
-			append_leaks(photon, photon->n_energies, lrec, n_rec);
-		free(lrec);
-	} else {
-		rc = pcb_unit_trace(in, ix, &irefl, p->z, p->cap, p->ext, cap_x, cap_y, p->nmax, n_shells == 0., ec.data(), (int)photon->n_energies,
-				    description->sig_rough, photon->weight, out);
+		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc=true is served by polycap_photon_launch / polycap_source_get_transmission_efficiencies", W);
+		return -1;
 	}
+	int rc = pcb_unit_trace(in, ix, &irefl, p->z, p->cap, p->ext, cap_x, cap_y, p->nmax, n_shells == 0., ec.data(), (int)photon->n_energies,
+				description->sig_rough, photon->weight, out);
 	if (unit_failed(rc, error, W))
 		return -1;
 	polycap_norm(&photon->start_direction); /* capil.c:1237 */
@@ -1131,14 +1098,19 @@ extern "C" int polycap_capil_trace_wall(polycap_photon *photon, double *d_travel
 	if (photon == NULL) { polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: photon cannot be NULL", W); return -1; }
 	if (photon->description == NULL) { polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: description cannot be NULL", W); return -1; }
 	if (!d_travel || !capx_id || !capy_id) { polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: output pointers cannot be NULL", W); return -1; }
-	const polycap_description *d = photon->description;
-	const polycap_profile *p = d->profile;
+	polycap_description *d = photon->description;
 	const double in[6] = {photon->exit_coords.x, photon->exit_coords.y, photon->exit_coords.z,
 			      photon->exit_direction.x, photon->exit_direction.y, photon->exit_direction.z};
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
-	int rc = pcb_unit_trace_wall(in, p->z, p->cap, p->ext, p->nmax, d->n_cap, d_travel, capx_id, capy_id);
-	if (unit_failed(rc, error, W))
+	double e10 = 10.0, one = 1.0; /* the wall march is energy independent: any valid energy keys the optic */
+	pcb_gpu_optic *g = optic_for(d, 1, &e10, &one, &one, -1, error, W);
+	if (!g)
 		return -1;
+	int rc = pcb_gpu_leak_trace_wall(g, in, d_travel, capx_id, capy_id);
+	if (rc == -1 && *pcb_gpu_last_error()) {
+		gpu_fail(error, W);
+		return -1;
+	}
 	polycap_norm(&photon->exit_direction); /* capil.c:919 */
 	return rc;
 }
@@ -1185,6 +1157,12 @@ extern "C" bool polycap_b200_optical_constants(polycap_description *description,
 	return true;
 }
 
+static bool launch_batch_impl(const char *W, polycap_description *description, size_t n_energies, const double *energies, const double *amu,
+			      const double *scatf, int64_t n, const double *start_coords, const double *start_direction, const double *start_electric_vector,
+			      bool leak_calc, int *ret, double *exit_coords, double *exit_direction, double *exit_electric_vector, int64_t *i_refl,
+			      double *d_travel, double *weights, int64_t *counters, int64_t *leak_count, double **leak_records, int64_t *n_leak_records,
+			      polycap_error **error);
+
 extern "C" bool polycap_b200_photon_launch_batch(polycap_description *description, size_t n_energies, const double *energies, const double *amu,
 						 const double *scatf, int64_t n, const double *start_coords, const double *start_direction,
 						 const double *start_electric_vector, bool leak_calc, int *ret, double *exit_coords, double *exit_direction,
@@ -1202,8 +1180,44 @@ extern "C" bool polycap_b200_photon_launch_batch(polycap_description *descriptio
 			return false;
 		}
 	if (leak_calc) {
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc is served per photon by polycap_photon_launch", W);
+		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: use polycap_b200_photon_launch_batch_leaks for leak_calc = true", W);
 		return false;
+	}
+	return launch_batch_impl(W, description, n_energies, energies, amu, scatf, n, start_coords, start_direction, start_electric_vector, false, ret,
+				 exit_coords, exit_direction, exit_electric_vector, i_refl, d_travel, weights, counters, NULL, NULL, NULL, error);
+}
+
+extern "C" bool polycap_b200_photon_launch_batch_leaks(polycap_description *description, size_t n_energies, const double *energies, const double *amu,
+						       const double *scatf, int64_t n, const double *start_coords, const double *start_direction,
+						       const double *start_electric_vector, int *ret, double *exit_coords, double *exit_direction,
+						       double *exit_electric_vector, int64_t *i_refl, double *d_travel, double *weights,
+						       int64_t *leak_count, double **leak_records, int64_t *n_leak_records, polycap_error **error)
+{
+	static const char *W = "polycap_b200_photon_launch_batch_leaks";
+	if (!description || !energies || n_energies < 1 || n < 0 || !leak_count || !leak_records || !n_leak_records ||
+	    (n > 0 && (!start_coords || !start_direction || !start_electric_vector))) {
+		polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: NULL argument, n_energies < 1 or n < 0", W);
+		return false;
+	}
+	for (size_t i = 0; i < n_energies; i++)
+		if (energies[i] < 1. || energies[i] > 100.) {
+			polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: energies[i] must be greater than 1 and less than 100", W);
+			return false;
+		}
+	return launch_batch_impl(W, description, n_energies, energies, amu, scatf, n, start_coords, start_direction, start_electric_vector, true, ret,
+				 exit_coords, exit_direction, exit_electric_vector, i_refl, d_travel, weights, NULL, leak_count, leak_records, n_leak_records,
+				 error);
+}
+
+static bool launch_batch_impl(const char *W, polycap_description *description, size_t n_energies, const double *energies, const double *amu,
+			      const double *scatf, int64_t n, const double *start_coords, const double *start_direction, const double *start_electric_vector,
+			      bool leak_calc, int *ret, double *exit_coords, double *exit_direction, double *exit_electric_vector, int64_t *i_refl,
+			      double *d_travel, double *weights, int64_t *counters, int64_t *leak_count, double **leak_records, int64_t *n_leak_records,
+			      polycap_error **error)
+{
+	if (leak_records) {
+		*leak_records = NULL;
+		*n_leak_records = 0;
 	}
 	if (n == 0) {
 		if (counters)
@@ -1223,7 +1237,10 @@ extern "C" bool polycap_b200_photon_launch_batch(polycap_description *descriptio
 		wtmp.resize((size_t)n * n_energies);
 		w = wtmp.data();
 	}
-	if (pcb_gpu_replay(g, n, start_coords, start_direction, start_electric_vector, r.data(), st.data(), ir.data(), w, counters)) {
+	int rc = leak_calc ? pcb_gpu_replay_leak(g, n, start_coords, start_direction, start_electric_vector, r.data(), st.data(), ir.data(), w, counters, leak_count,
+						 leak_records, n_leak_records)
+			   : pcb_gpu_replay(g, n, start_coords, start_direction, start_electric_vector, r.data(), st.data(), ir.data(), w, counters);
+	if (rc) {
 		gpu_fail(error, W);
 		return false;
 	}

@@ -78,6 +78,15 @@ int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, 
 /* start state the tracer draws for ids [id0, id0+n): out[n][11] = coords(3) dir(3) elecv(3) src_x src_y (host memory) */
 int pcb_gpu_sample_ids(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n, double *out_host);
 
+/* leak_calc = true (pcb_leak.cu): replay / source wave with leak records, and the single-item wall march.
+ * leak_rec: malloc'd [n_leak_rec][11+nE] = kind (0 ext, 1 int), coords(3), direction(3), elecv(3), n_refl, weights(nE), photon order. */
+int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state, int64_t *irefl,
+			double *weights, int64_t *counters, int64_t *leak_count /* [n][2] */, double **leak_rec, int64_t *n_leak_rec);
+int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted, double *d_sum_weights,
+			  int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap, int64_t rec_base, int64_t *ids_used,
+			  int64_t *n_exit, double **leak_rec, int64_t *n_leak_rec);
+int pcb_gpu_leak_trace_wall(pcb_gpu_optic *g, const double in[6], double *d_travel, int *r_cntr, int *q_cntr);
+
 /* dense per-id view of the last wave (debug / parity): status[n] and the 17+nE record of every id */
 int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, double *rec /* [n][17+nE] or NULL */);
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "pcb_gpu.h"
+#include "pcb_leak.h"
 #include "pcb_trace.cuh"
 
 extern "C" void pcb_energy_constants(size_t n_energies, const double *energies, const double *amu, const double *scatf, double density, double *out);
@@ -67,6 +68,7 @@ struct pcb_gpu_optic {
 	int thr_cand = 12, thr_refl = 12, thr_new = 8;
 	int tables_in_smem = 1;
 	int exact_weights = 0;
+	int monotonic = 1; /* z strictly increasing */
 	double cap0 = 0, ext0 = 0;
 	/* wave buffers (grown on demand) */
 	int64_t wave_cap = 0;
@@ -172,6 +174,9 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	for (int i = 0; i + 1 < n; i++)
 		if (!(d->z[i + 1] > d->z[i]))
 			m_safe = -1; /* non-monotonic z: only the exact path is trusted */
+	for (int i = 0; i + 1 < n; i++)
+		if (!(d->z[i + 1] > d->z[i]))
+			g->monotonic = 0;
 
 	PcbOptic &o = g->o;
 	o.nmax = d->nmax;
@@ -686,19 +691,10 @@ __global__ void wave_compact_weights(const int8_t *status, const int64_t *rank, 
 	}
 }
 
-extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
-				double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap,
-				int64_t rec_base, void *stream_v, int64_t *ids_used, int64_t *n_exit)
+/* id-ordered post-processing of the dense per-id outputs in g->d_status/d_irefl/d_fields/d_weights (see file header) */
+static int wave_post(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *d_sum_weights, int64_t *d_counters, double *d_rec_fields,
+		     double *d_rec_weights, int64_t rec_cap, int64_t rec_base, cudaStream_t stream, int64_t *ids_used, int64_t *n_exit)
 {
-	cudaStream_t stream = (cudaStream_t)stream_v;
-	if (n_ids <= 0)
-		return 0;
-	CK(cudaSetDevice(g->device));
-	if (ensure_wave(g, n_ids))
-		return -1;
-	PcbReplayIn rin{};
-	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, stream))
-		return -1;
 	g->last_wave_n = n_ids;
 	const int nb = (int)((n_ids + SCAN_T - 1) / SCAN_T);
 	if (nb > (1 << 16)) {
@@ -734,6 +730,140 @@ extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint
 			*n_exit = ci[1];
 	}
 	return 0;
+}
+
+extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
+				double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap,
+				int64_t rec_base, void *stream_v, int64_t *ids_used, int64_t *n_exit)
+{
+	cudaStream_t stream = (cudaStream_t)stream_v;
+	if (n_ids <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	if (ensure_wave(g, n_ids))
+		return -1;
+	PcbReplayIn rin{};
+	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, stream))
+		return -1;
+	return wave_post(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, ids_used, n_exit);
+}
+
+/* ------------------------------------------------------------------ leak_calc = true (pcb_leak.cu) */
+
+static void leak_view(const pcb_gpu_optic *g, pcb_leak_optic *v)
+{
+	v->nmax = g->nmax; v->nE = g->nE; v->mono = g->o.mono; v->monotonic = g->monotonic; v->sm_count = g->sm_count; v->device = g->device;
+	v->n_shells = g->o.n_shells; v->sig_rough = g->o.sig_rough; v->cap0 = g->cap0; v->ext0 = g->ext0;
+	v->d_z = g->o.z; v->d_cap = g->o.cap; v->d_ext = g->o.ext; v->d_hexz = g->o.hexz; v->d_ec = g->o.ec;
+}
+
+extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state,
+				   int64_t *irefl, double *weights, int64_t *counters, int64_t *leak_count, double **leak_rec, int64_t *n_leak_rec)
+{
+	*leak_rec = nullptr;
+	*n_leak_rec = 0;
+	if (n <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	pcb_leak_optic v;
+	leak_view(g, &v);
+	std::vector<int8_t> st((size_t)n);
+	std::vector<int> ir((size_t)n), ln((size_t)n);
+	std::vector<double> f((size_t)n * 11);
+	int64_t refl = 0;
+	if (pcb_leak_run(&v, nullptr, 0, 0, n, coords, dir, ev, st.data(), ir.data(), f.data(), weights, ln.data(), leak_rec, n_leak_rec, &refl)) {
+		g_last_error = pcb_leak_last_error();
+		return -1;
+	}
+	g->n_kernels++;
+	const size_t stride = 11 + (size_t)g->nE;
+	size_t r = 0;
+	for (int64_t i = 0; i < n; i++) {
+		ret[i] = st[i];
+		irefl[i] = ir[i];
+		for (int k = 0; k < 11; k++)
+			out_state[i * 11 + k] = f[(size_t)k * n + i];
+		if (leak_count) {
+			leak_count[2 * i] = leak_count[2 * i + 1] = 0;
+			for (int k = 0; k < ln[i]; k++, r++)
+				leak_count[2 * i + ((*leak_rec)[r * stride] == 0. ? 0 : 1)]++;
+		}
+	}
+	if (counters) {
+		memset(counters, 0, PCB_C_COUNT * 8);
+		counters[PCB_C_IDS] = n;
+		counters[PCB_C_REFL_ALL] = refl;
+		counters[PCB_C_LAUNCHED] = n;
+	}
+	return 0;
+}
+
+extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
+				     double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap,
+				     int64_t rec_base, int64_t *ids_used, int64_t *n_exit, double **leak_rec, int64_t *n_leak_rec)
+{
+	*leak_rec = nullptr;
+	*n_leak_rec = 0;
+	if (n_ids <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	if (ensure_wave(g, n_ids))
+		return -1;
+	pcb_leak_optic v;
+	leak_view(g, &v);
+	const size_t nE = (size_t)g->nE;
+	std::vector<int8_t> st((size_t)n_ids);
+	std::vector<int> ir((size_t)n_ids), ln((size_t)n_ids);
+	std::vector<double> f((size_t)n_ids * 17), w((size_t)n_ids * nE);
+	double *recs = nullptr;
+	int64_t nrec = 0, refl = 0;
+	if (pcb_leak_run(&v, s, seed, id0, n_ids, nullptr, nullptr, nullptr, st.data(), ir.data(), f.data(), w.data(), ln.data(), &recs, &nrec, &refl)) {
+		g_last_error = pcb_leak_last_error();
+		return -1;
+	}
+	g->n_kernels++;
+	/* same id-ordered post-processing as the plain path, over the leak kernel's dense outputs */
+	cudaStream_t stream = 0;
+	PcbWorkCounters wc{};
+	wc.reflections = (unsigned long long)refl;
+	wc.launched = (unsigned long long)n_ids;
+	bool ok = cudaMemcpy(g->d_status, st.data(), (size_t)n_ids, cudaMemcpyHostToDevice) == cudaSuccess &&
+		  cudaMemcpy(g->d_irefl, ir.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+		  cudaMemcpy(g->d_fields, f.data(), f.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+		  cudaMemcpy(g->d_weights, w.data(), w.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+		  cudaMemcpy(g->d_wc, &wc, sizeof wc, cudaMemcpyHostToDevice) == cudaSuccess;
+	if (!ok) {
+		free(recs);
+		g_last_error = "leak wave: device upload failed";
+		return -1;
+	}
+	int64_t used = 0, got = 0;
+	if (wave_post(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, &used, &got)) {
+		free(recs);
+		return -1;
+	}
+	if (ids_used)
+		*ids_used = used;
+	if (n_exit)
+		*n_exit = got;
+	/* leak records of the ids below the cut */
+	int64_t keep = 0;
+	for (int64_t i = 0; i < used; i++)
+		keep += ln[(size_t)i];
+	*leak_rec = recs;
+	*n_leak_rec = keep;
+	return 0;
+}
+
+extern "C" int pcb_gpu_leak_trace_wall(pcb_gpu_optic *g, const double in[6], double *d_travel, int *r_cntr, int *q_cntr)
+{
+	CK(cudaSetDevice(g->device));
+	pcb_leak_optic v;
+	leak_view(g, &v);
+	int rc = pcb_leak_unit_trace_wall(&v, in, d_travel, r_cntr, q_cntr);
+	if (rc == -1 && *pcb_leak_last_error())
+		g_last_error = pcb_leak_last_error();
+	return rc;
 }
 
 extern "C" int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, double *rec)
