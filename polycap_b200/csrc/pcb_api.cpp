@@ -95,10 +95,14 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 		h = fnv(h, v ? v : "", v ? strlen(v) + 1 : 1);
 	}
 	CachedOptic *slot = &g_cache[0];
-	const bool no_cache = getenv("POLYCAP_B200_NO_CACHE") != NULL; /* re-upload the tables on every call (end-to-end timing) */
+	const bool no_cache = getenv("POLYCAP_B200_REUPLOAD") != NULL; /* re-send tables + constants on every call (end-to-end timing) */
 	for (auto &c : g_cache) {
-		if (c.g && c.key == h && !no_cache) {
+		if (c.g && c.key == h) {
 			c.stamp = ++g_stamp;
+			if (no_cache && pcb_gpu_optic_reupload(c.g, NULL)) { /* inputs travel host -> device on every call */
+				polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: CUDA failure: %s", who, pcb_gpu_last_error());
+				return nullptr;
+			}
 			return c.g;
 		}
 		if (c.stamp < slot->stamp)
@@ -634,20 +638,24 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 
 	std::vector<double> sum(nE);
 	int64_t cnt[PCB_C_COUNT];
-	std::vector<double> rf((size_t)want * 17);
 	polycap_transmission_efficiencies *eff = (polycap_transmission_efficiencies *)calloc(1, sizeof(*eff));
 	eff->images = (struct _polycap_images *)calloc(1, sizeof(struct _polycap_images));
 	struct _polycap_images *im = eff->images;
 	im->exit_coord_weights = (double *)malloc(sizeof(double) * (size_t)want * nE);
-	bool ok = pcb_gpu_copy_to_host(dev, sum.data(), d_sum, nE * 8, NULL) == 0 && pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0 &&
-		  pcb_gpu_copy_to_host(dev, rf.data(), d_rf, rf.size() * 8, NULL) == 0 &&
-		  pcb_gpu_copy_to_host(dev, im->exit_coord_weights, d_rw, (size_t)want * nE * 8, NULL) == 0;
+	/* device -> pinned staging (one DMA per array at PCIe speed) -> the caller-owned arrays of struct _polycap_images */
+	const size_t rf_bytes = (size_t)want * 17 * 8, rw_bytes = (size_t)want * nE * 8;
+	double *stage = (double *)pcb_gpu_optic_stage(g, rf_bytes + rw_bytes);
+	bool ok = stage != NULL && pcb_gpu_copy_to_host(dev, sum.data(), d_sum, nE * 8, NULL) == 0 &&
+		  pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0 && pcb_gpu_copy_to_host(dev, stage, d_rf, rf_bytes, NULL) == 0 &&
+		  pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, d_rw, rw_bytes, NULL) == 0;
 	cleanup();
 	if (!ok) {
 		gpu_fail(error, WHO);
 		polycap_transmission_efficiencies_free(eff);
 		return NULL;
 	}
+	const double *rf = stage;
+	memcpy(im->exit_coord_weights, stage + (size_t)want * 17, rw_bytes);
 	/* unpack the 17 record fields (struct _polycap_images, private.h:156-181) */
 	double **dst[16] = {&im->src_start_coords[0], &im->src_start_coords[1], &im->pc_start_coords[0], &im->pc_start_coords[1], &im->pc_start_dir[0],
 			    &im->pc_start_dir[1], &im->pc_start_elecv[0], &im->pc_start_elecv[1], &im->pc_exit_coords[0], &im->pc_exit_coords[1],
@@ -655,7 +663,7 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	const int src_field[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16};
 	for (int f = 0; f < 16; f++) {
 		*dst[f] = (double *)malloc(sizeof(double) * (size_t)want);
-		memcpy(*dst[f], rf.data() + (size_t)src_field[f] * want, sizeof(double) * (size_t)want);
+		memcpy(*dst[f], rf + (size_t)src_field[f] * want, sizeof(double) * (size_t)want);
 	}
 	im->pc_exit_nrefl = (int64_t *)malloc(sizeof(int64_t) * (size_t)want);
 	for (int64_t i = 0; i < want; i++)

@@ -55,6 +55,11 @@ int pcb_gpu_optic_n_energies(const pcb_gpu_optic *g);
 /* Tuning knobs (phase-vote thresholds in lanes, CTAs per SM, exact-check mode); <0 keeps the default. */
 void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl, int thr_new, int ctas_per_sm, int all_slow);
 
+/* pinned-memory plumbing: re-send the optic's inputs (H2D), bytes of those inputs, grow-only pinned staging area for results */
+int pcb_gpu_optic_reupload(pcb_gpu_optic *g, void *stream);
+size_t pcb_gpu_optic_input_bytes(const pcb_gpu_optic *g);
+void *pcb_gpu_optic_stage(pcb_gpu_optic *g, size_t bytes);
+
 /* instrumentation (bench.py): CUDA-event timing of the trace kernels, kernel-launch counts */
 void pcb_gpu_optic_timing(pcb_gpu_optic *g, int on);
 int64_t pcb_gpu_optic_kernels(const pcb_gpu_optic *g, int64_t *n_trace);

@@ -69,6 +69,11 @@ struct pcb_gpu_optic {
 	int tables_in_smem = 1;
 	int exact_weights = 0;
 	int monotonic = 1; /* z strictly increasing */
+	/* pinned host memory: the staged tables/constants (re-uploadable) and a grow-only staging area for results */
+	double *h_tables = nullptr, *h_ec = nullptr;
+	size_t ec_bytes = 0;
+	void *h_stage = nullptr;
+	size_t h_stage_bytes = 0;
 	double cap0 = 0, ext0 = 0;
 	/* wave buffers (grown on demand) */
 	int64_t wave_cap = 0;
@@ -194,9 +199,16 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 
 	bool ok = cudaMalloc(&g->d_tables, 5 * tb) == cudaSuccess && cudaMalloc(&g->d_ec, ec.size() * 8) == cudaSuccess &&
 		  cudaMalloc(&g->d_wc, sizeof(PcbWorkCounters)) == cudaSuccess;
+	g->ec_bytes = ec.size() * 8;
 	if (ok)
-		ok = cudaMemcpy(g->d_tables, h.data(), 5 * tb, cudaMemcpyHostToDevice) == cudaSuccess &&
-		     cudaMemcpy(g->d_ec, ec.data(), ec.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+		ok = cudaHostAlloc((void **)&g->h_tables, 5 * tb, cudaHostAllocDefault) == cudaSuccess &&
+		     cudaHostAlloc((void **)&g->h_ec, g->ec_bytes, cudaHostAllocDefault) == cudaSuccess;
+	if (ok) {
+		memcpy(g->h_tables, h.data(), 5 * tb);
+		memcpy(g->h_ec, ec.data(), g->ec_bytes);
+		ok = cudaMemcpy(g->d_tables, g->h_tables, 5 * tb, cudaMemcpyHostToDevice) == cudaSuccess &&
+		     cudaMemcpy(g->d_ec, g->h_ec, g->ec_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+	}
 	if (!ok) {
 		g_last_error = std::string("device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError());
 		pcb_gpu_optic_destroy(g);
@@ -229,6 +241,9 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights);
 	cudaFree(g->d_rank); cudaFree(g->d_blocksum); cudaFree(g->d_cutinfo); cudaFree(g->d_partial); cudaFree(g->d_cpartial);
 	cudaFree(g->d_rin);
+	cudaFreeHost(g->h_tables);
+	cudaFreeHost(g->h_ec);
+	cudaFreeHost(g->h_stage);
 	for (auto &p : g->ev_pending) {
 		cudaEventDestroy(p.first);
 		cudaEventDestroy(p.second);
@@ -236,6 +251,35 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	for (auto &e : g->ev_pool)
 		cudaEventDestroy(e);
 	delete g;
+}
+
+/* re-send the tables and per-energy constants from pinned host memory (end-to-end timing: inputs travel every call) */
+extern "C" int pcb_gpu_optic_reupload(pcb_gpu_optic *g, void *stream_v)
+{
+	cudaStream_t stream = (cudaStream_t)stream_v;
+	CK(cudaSetDevice(g->device));
+	CK(cudaMemcpyAsync(g->d_tables, g->h_tables, 5 * g->table_bytes, cudaMemcpyHostToDevice, stream));
+	CK(cudaMemcpyAsync(g->d_ec, g->h_ec, g->ec_bytes, cudaMemcpyHostToDevice, stream));
+	return 0;
+}
+extern "C" size_t pcb_gpu_optic_input_bytes(const pcb_gpu_optic *g) { return 5 * g->table_bytes + g->ec_bytes; }
+
+/* grow-only pinned staging area owned by the optic (device -> host result copies run at PCIe speed from here) */
+extern "C" void *pcb_gpu_optic_stage(pcb_gpu_optic *g, size_t bytes)
+{
+	if (bytes <= g->h_stage_bytes)
+		return g->h_stage;
+	cudaSetDevice(g->device);
+	cudaFreeHost(g->h_stage);
+	g->h_stage = nullptr;
+	g->h_stage_bytes = 0;
+	if (cudaHostAlloc(&g->h_stage, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		g_last_error = "cudaHostAlloc failed for the result staging area";
+		g->h_stage = nullptr;
+		return nullptr;
+	}
+	g->h_stage_bytes = bytes;
+	return g->h_stage;
 }
 
 /* ---- instrumentation ---- */
