@@ -31,7 +31,8 @@ struct PcbOptic {
 	double n_shells;
 	double sig_rough;
 	double hex_den;    /* 2*cos(pi/6)*(n_shells+1) */
-	double m_safe;     /* capillaries with max|n_j.(A,B)| < m_safe never leave the hexagon */
+	double m_safe;     /* capillaries with max|n_j.(A,B)| < m_safe never leave the hexagon (restart margin for tan(theta) <= 0.01) */
+	double m_deep;     /* ... < m_deep: the same with the margin for tan(theta) <= 0.25 */
 	const double *z, *cap, *ext, *hexz, *rm; /* global copies of the tables */
 	const double *ec;  /* [EC_ROWS][n_energies] */
 };

@@ -149,7 +149,7 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	std::vector<double> h(5 * tn, 0.0);
 	double *hz = h.data(), *hcap = hz + tn, *hext = hcap + tn, *hhex = hext + tn, *hrm = hhex + tn;
 	const double eps = 1e-9;
-	double m_safe = 1e300;
+	double m_safe = 1e300, m_deep = 1e300;
 	bool mono_ok = true;
 	for (int i = 0; i < n; i++) {
 		hz[i] = d->z[i];
@@ -159,16 +159,21 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 		hrm[i] = d->cap[i] * d->cap[i] * (1.0 - eps);
 		double apo = sqrt((d->ext[i] * d->ext[i]) - ((d->ext[i] / 2.) * (d->ext[i] / 2.)));
 		/* interior capillary: bore wall plus the largest lateral excursion of a back-extrapolated restart point
-		 * (one segment length at tan(theta) <= 0.25, see trace_begin) stays inside the outer hexagon at every z */
+		 * (one segment length at tan(theta) <= 0.01, see trace_begin) stays inside the outer hexagon at every z */
 		double dzmax = 0;
 		if (i > 0) dzmax = fmax(dzmax, d->z[i] - d->z[i - 1]);
 		if (i + 1 < n) dzmax = fmax(dzmax, d->z[i + 1] - d->z[i]);
-		double room = (apo * (1.0 - eps) - d->cap[i] - 0.25 * dzmax) / hhex[i];
+		double room = (apo * (1.0 - eps) - d->cap[i] - 0.01 * dzmax) / hhex[i];
+		double room_deep = (apo * (1.0 - eps) - d->cap[i] - 0.25 * dzmax) / hhex[i];
+		if (!(room_deep < 1e300))
+			room_deep = -1;
+		if (room_deep < m_deep)
+			m_deep = room_deep;
 		if (!(room < 1e300))
 			room = -1;
 		if (room < m_safe)
 			m_safe = room;
-		if (!(d->cap[i] + 0.25 * dzmax < apo * (1.0 - eps) && d->cap[i] < d->ext[i] * (1.0 - eps) && d->cap[i] * d->cap[i] < d->ext[i] * (1.0 - eps)))
+		if (!(d->cap[i] + 0.01 * dzmax < apo * (1.0 - eps) && d->cap[i] < d->ext[i] * (1.0 - eps) && d->cap[i] * d->cap[i] < d->ext[i] * (1.0 - eps)))
 			mono_ok = false;
 		if (!(d->cap[i] > 0) || !(d->ext[i] > 0))
 			m_safe = -1;
@@ -193,6 +198,7 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	o.sig_rough = d->sig_rough;
 	o.hex_den = 2. * COSPI_6_HOST * (n_shells + 1);
 	o.m_safe = o.mono ? (mono_ok && m_safe > 0 ? 1.0 : -1.0) : m_safe * (1.0 - eps);
+	o.m_deep = (m_safe > 0 && !o.mono) ? m_deep * (1.0 - eps) : -1.0;
 
 	std::vector<double> ec((size_t)EC_ROWS * g->nE);
 	pcb_energy_constants(d->n_energies, d->energies, d->amu, d->scatf, d->density, ec.data());

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 	double snx = 0, sny = 0, snz = 0, cosalfa = 0;
 	double dtrav = 0, A = 0, B = 0, inv_dz = 0;
 	int irefl = 0, ix = 0, iseg = 0, ntrace = 0, code = 0;
-	bool slow = false, w_init = false, in_cur = false, in_nxt = false;
+	bool slow = false, deep = false, w_init = false, in_cur = false, in_nxt = false;
 	unsigned int c_steps = 0, c_solves = 0, c_refl = 0, c_launch = 0;
 	bool ids_left = true;
 
@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 			 * Restarting on the wall the same holds from the hit point on: distance-to-axis minus radius is convex in z,
 			 * zero at the hit and negative at z[iseg+1], and the root at the hit itself is rejected by the reference's
 			 * 1e-5 forward margin (capil.c:134-156).  The back-extrapolated point at z[iseg], which the reference tests
-			 * against the outer hexagon (capil.c:1296-1308), lies at most dz*tan(theta) beyond the wall: inside the
+			 * against the outer hexagon (capil.c:1296-1308), lies at most dz*tan(theta) beyond the wall (<= 0.01 dz, or <= 0.25 dz for capillaries deep inside): inside the
 			 * hexagon for interior capillaries (m_safe carries that margin) unless the photon is steep. */
-			const bool steep = (dx * dx + dy * dy) > 0.0625 * (dz * dz);
+			const bool steep = (dx * dx + dy * dy) > (deep ? 0.0625 : 1.e-4) * (dz * dz); /* tan(theta) > 0.25 (deep inside) or 0.01 */
 			if (on_wall && !steep) {
 				in_cur = true;
 			} else {
@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 						double m1 = fabs(B), m2 = fabs(PCB_COSPI_6 * A + 0.5 * B), m3 = fabs(PCB_COSPI_6 * A - 0.5 * B);
 						double mm = fmax(m1, fmax(m2, m3));
 						slow = o.all_slow || !(mm < o.m_safe);
+						deep = mm < o.m_deep;
 						trace_begin(false);
 					}
 				}
