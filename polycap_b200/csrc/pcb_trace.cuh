@@ -393,8 +393,61 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 				__syncwarp();
 				int pi = lane / nE, e = lane - pi * nE; /* pair index -> (rank of photon among `go`, energy) */
 				const int dpi = 32 / nE, de = 32 - dpi * nE;
-				/* software pipeline: the weight of the next pair is loaded while the current one is evaluated */
-				bool valid = lane < total;
+				int j0 = 0;
+				/* rounds of 64 pairs while they last: two independent evaluations per lane keep the FP64 pipe busy across
+				 * the dependency chains of one (4 warps per scheduler cannot hide them alone) */
+				if (!EXACT_W) {
+#ifndef PCB_ILP
+#define PCB_ILP 2
+#endif
+					enum { U = PCB_ILP };
+					int pu[U], eu[U];
+					pu[0] = pi; eu[0] = e;
+#pragma unroll
+					for (int u = 1; u < U; u++) {
+						pu[u] = pu[u - 1] + dpi; eu[u] = eu[u - 1] + de;
+						if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
+					}
+					const int dpiU = (32 * U) / nE, deU = 32 * U - dpiU * nE;
+					for (; j0 + 32 * U <= total; j0 += 32 * U) {
+						const double *q[U];
+						double *wp[U];
+						double w[U], r[U];
+						int sl[U];
+#pragma unroll
+						for (int u = 0; u < U; u++) {
+							q[u] = stg + pu[u] * STG_N;
+							const double tag = q[u][5];
+							sl[u] = __double2loint(tag);
+							wp[u] = wwarp + (unsigned long long)sl[u] * nE + eu[u];
+							w[u] = __double2hiint(tag) ? *wp[u] : 1.0;
+						}
+#pragma unroll
+						for (int u = 0; u < U; u++)
+							r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
+										 __ldg(ec + EC_I2IM * nE + eu[u]), q[u][0], q[u][1], q[u][2], q[u][3]);
+#pragma unroll
+						for (int u = 0; u < U; u++) {
+							if (rough) {
+								const double cr = __ldg(ec + EC_KR * nE + eu[u]) * q[u][4] * sig_rough;
+								w[u] = w[u] * r[u] * exp(-1. * cr * cr);
+							} else {
+								w[u] = w[u] * r[u] * 1.0;
+							}
+							*wp[u] = w[u];
+							if (r[u] < 0. || r[u] > 1.)
+								bad_bits |= 1u << sl[u];
+							if (w[u] >= 1.e-4)
+								alive_bits |= 1u << sl[u];
+							pu[u] += dpiU; eu[u] += deU;
+							if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
+						}
+					}
+					pi = pu[0];
+					e = eu[0];
+				}
+				/* remainder: one pair per lane and round, the weight of the next pair loaded while the current one is evaluated */
+				bool valid = (j0 + lane) < total;
 				int src = 0, winit = 0;
 				double w_next = 1.0;
 				if (valid) {
@@ -404,7 +457,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 					if (winit)
 						w_next = wwarp[(unsigned long long)src * nE + e];
 				}
-				for (int j0 = 0; j0 < total; j0 += 32) {
+				for (; j0 < total; j0 += 32) {
 					const bool v_cur = valid;
 					const int src_cur = src, e_cur = e, pi_cur = pi;
 					double w = w_next;
