@@ -430,6 +430,12 @@ extern "C" int polycap_photon_launch(polycap_photon *photon, size_t n_energies, 
 		}
 	}
 	free(lrec);
+	if (ret == -2) { /* photon.c:519,555 */
+		const double n_shells = round(sqrt(12. * d->n_cap - 3.) / 6. - 0.5);
+		polycap_set_error_literal(error, POLYCAP_ERROR_INVALID_ARGUMENT,
+					  n_shells == 0. ? "polycap_photon_launch: photon_pos_check: photon not within monocapillary boundaries"
+							 : "polycap_photon_launch: photon_pos_check: photon not within optic boundaries");
+	}
 	/* photon.c:930-945: energies/weight/amu/scatf are NULL on return (this library never attaches them in launch) */
 	free(photon->energies); photon->energies = NULL;
 	free(photon->weight); photon->weight = NULL;

@@ -303,7 +303,11 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 					}
 				}
 			}
-		} else if (phase == LS_REFL) {
+			/* a solve that hits is followed at once by the reflection: no second vote between the two */
+			if (__any_sync(0xffffffffu, st == LS_REFL))
+				phase = LS_REFL;
+		}
+		if (phase == LS_REFL) {
 			/* ---------------- REFL: travel, checks, Fresnel update, specular direction ---------------- */
 			bool mine = (st == LS_REFL);
 			ReflGeom g;
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 				}
 				st = LS_NEW;
 			}
-		} else {
+		} else if (phase == LS_NEW) {
 			/* ---------------- NEW: fetch an id, build the start state, launch ---------------- */
 			bool want = (st == LS_NEW);
 			unsigned m = __ballot_sync(0xffffffffu, want && ids_left);
