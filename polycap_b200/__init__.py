@@ -33,7 +33,8 @@ c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
 
 N_COUNTERS = 16
-COUNTER_NAMES = ("ids", "exit", "not_entered", "not_transmitted", "uncounted", "refl_exit", "refl_all", "seg_steps", "solves", "launched")
+COUNTER_NAMES = ("ids", "exit", "not_entered", "not_transmitted", "uncounted", "refl_exit", "refl_all", "seg_steps", "solves", "launched",
+                 "q_batches", "q_lanes", "q_empty_polls", "q_lost_races", "q_hit_batches", "q_hit_lanes")
 
 
 class _Vec3(C.Structure):

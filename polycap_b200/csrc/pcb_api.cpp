@@ -90,7 +90,7 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 	h = fnv(h, amu.data(), nE * 8);
 	h = fnv(h, scatf.data(), nE * 8);
 	h = fnv(h, &device, sizeof device);
-	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS"}) { /* modes read at optic creation */
+	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS", "POLYCAP_B200_KERNEL"}) { /* modes read at optic creation */
 		const char *v = getenv(k);
 		h = fnv(h, v ? v : "", v ? strlen(v) + 1 : 1);
 	}

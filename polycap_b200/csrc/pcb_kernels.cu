@@ -22,6 +22,7 @@
 #include "pcb_gpu.h"
 #include "pcb_leak.h"
 #include "pcb_trace.cuh"
+#include "pcb_trace2.cuh"
 
 extern "C" void pcb_energy_constants(size_t n_energies, const double *energies, const double *amu, const double *scatf, double density, double *out);
 
@@ -68,6 +69,7 @@ struct pcb_gpu_optic {
 	int thr_cand = 12, thr_refl = 12, thr_new = 8;
 	int tables_in_smem = 1;
 	int exact_weights = 0;
+	int kernel_version = 2; /* 2: CTA task-queue tracer (pcb_trace2.cuh, default), 1: warp-voted tracer (pcb_trace.cuh) */
 	int monotonic = 1; /* z strictly increasing */
 	/* pinned host memory: the staged tables/constants (re-uploadable) and a grow-only staging area for results */
 	double *h_tables = nullptr, *h_ec = nullptr;
@@ -235,6 +237,9 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	if ((e = getenv("POLYCAP_B200_THR_NEW"))) g->thr_new = atoi(e);
 	if ((e = getenv("POLYCAP_B200_CTAS_PER_SM"))) g->ctas_per_sm = atoi(e);
 	if ((e = getenv("POLYCAP_B200_EXACT_FRESNEL"))) g->exact_weights = atoi(e);
+	if ((e = getenv("POLYCAP_B200_KERNEL"))) g->kernel_version = atoi(e);
+	if (t2_smem_bytes((int)tn) > 227 * 1024)
+		g->kernel_version = 1; /* profile too long for the shared-memory pool */
 	return g;
 }
 
@@ -353,6 +358,8 @@ static int ensure_wave(pcb_gpu_optic *g, int64_t n)
 {
 	if (!g->d_wscratch) {
 		size_t slots = (size_t)g->sm_count * g->ctas_per_sm * g->threads;
+		if (slots < (size_t)g->sm_count * T2_NP)
+			slots = (size_t)g->sm_count * T2_NP;
 		CK(cudaMalloc(&g->d_wscratch, slots * (size_t)g->nE * 8));
 	}
 	if (n <= g->wave_cap)
@@ -413,15 +420,28 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 	g->n_kernels++;
 	g->n_trace++;
 	/* EXACT_W = 1: per-energy Fresnel term in the reference's operation order (bit-level weights); 0: the cheap evaluation */
-#define PCB_LAUNCH(M, X)                                                                                                  \
-	do {                                                                                                              \
-		CK(cudaFuncSetAttribute(pcb_trace_kernel<M, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-		pcb_trace_kernel<M, X><<<blocks, g->threads, smem, stream>>>(P);                                          \
+#define PCB_LAUNCH(K, M, X)                                                                                     \
+	do {                                                                                                    \
+		CK(cudaFuncSetAttribute(K<M, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+		K<M, X><<<blocks, nthreads, smem, stream>>>(P);                                                 \
 	} while (0)
-	if (mode == MODE_SOURCE) {
-		if (g->exact_weights) PCB_LAUNCH(MODE_SOURCE, 1); else PCB_LAUNCH(MODE_SOURCE, 0);
+	int nthreads = g->threads;
+	if (g->kernel_version == 2) {
+		nthreads = T2_THREADS;
+		smem = t2_smem_bytes(g->o.tstride);
+		blocks = g->sm_count;
+		int64_t need2 = (n + T2_NP - 1) / T2_NP;
+		if (need2 < blocks)
+			blocks = (int)(need2 > 0 ? need2 : 1);
+		if (mode == MODE_SOURCE) {
+			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 1); else PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 0);
+		} else {
+			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 1); else PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 0);
+		}
+	} else if (mode == MODE_SOURCE) {
+		if (g->exact_weights) PCB_LAUNCH(pcb_trace_kernel, MODE_SOURCE, 1); else PCB_LAUNCH(pcb_trace_kernel, MODE_SOURCE, 0);
 	} else {
-		if (g->exact_weights) PCB_LAUNCH(MODE_REPLAY, 1); else PCB_LAUNCH(MODE_REPLAY, 0);
+		if (g->exact_weights) PCB_LAUNCH(pcb_trace_kernel, MODE_REPLAY, 1); else PCB_LAUNCH(pcb_trace_kernel, MODE_REPLAY, 0);
 	}
 #undef PCB_LAUNCH
 	if (g->timing) {
@@ -706,6 +726,8 @@ __global__ void wave_tally_final(const double *partial, const int64_t *cpartial,
 		counters[PCB_C_SOLVES] += (int64_t)wc->solves;
 		counters[PCB_C_LAUNCHED] += (int64_t)wc->launched;
 	}
+	if (t >= 10 && t < 16)
+		counters[t] += (int64_t)wc->dbg[t - 10]; /* scheduler statistics of the task-queue tracer: batches, lanes, empty polls, lost races, HIT batches, HIT lanes */
 }
 
 /* packed records: out_fields[f][rec_base + rank], out_weights[rec_base + rank][e] */
@@ -759,7 +781,7 @@ static int wave_post(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *
 	if (tb > nb)
 		tb = nb;
 	wave_tally_partial<<<tb, 256, 256 * 8, stream>>>(g->d_status, g->d_irefl, g->d_weights, g->nE, n_ids, g->d_cutinfo, g->d_partial, g->d_cpartial);
-	int ft = g->nE > 6 ? g->nE : 6;
+	int ft = g->nE > 16 ? g->nE : 16;
 	wave_tally_final<<<(ft + 255) / 256, 256, 0, stream>>>(g->d_partial, g->d_cpartial, tb, g->nE, g->d_cutinfo, g->d_wc, d_sum_weights, d_counters);
 	g->n_kernels += 6;
 	if (d_rec_fields && d_rec_weights) {

@@ -51,6 +51,7 @@ struct PcbWorkCounters { /* device-side work counters for the flop model (SURVEY
 	unsigned long long solves;      /* full quadratic solves */
 	unsigned long long reflections; /* capil_reflect events */
 	unsigned long long launched;    /* photons sampled/launched */
+	unsigned long long dbg[8];      /* scheduler statistics of the task-queue tracer: batches, lanes, empty polls, lost races, per type */
 };
 
 struct PcbTraceParams {

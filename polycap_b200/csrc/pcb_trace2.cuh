@@ -1,0 +1,769 @@
+/*
+ * pcb_trace2.cuh -- the CTA-level task-queue tracer (sm_100a, FP64): same arithmetic, different scheduling.
+ *
+ * pcb_trace.cuh keeps a photon in the registers of one lane and lets each warp vote on the phase to run, which
+ * leaves ~40 % of the lanes idle in the expensive phases (a photon spends most of its life waiting for or doing the
+ * wall-hit work, but the 32 photons of one warp are rarely there together).  Here a CTA owns a pool of T2_NP photons
+ * whose state lives in SHARED MEMORY, and one ring buffer per task type:
+ *
+ *   NEW   slot is free: fetch an id, sample / read the start state, launch logic      -> SCAN / DONE / (idle)
+ *   SCAN  walk segments with the convexity skip test until a candidate segment         -> HIT / DONE / SCAN
+ *   HIT   the reference's solve for the candidate; on a hit the whole reflection: travel /
+ *         in-optic checks, geometry, the per-energy Fresnel update with the batch's
+ *         (photon, energy) pairs dealt over all lanes, specular direction, next trace
+ *         call; then the scan to the next candidate while the photon is in registers   -> HIT / SCAN / DONE
+ *   DONE  classify, write the dense per-id outputs                                     -> NEW
+ *
+ * Every warp loops: pick a queue (one with >= 32 entries if there is one), claim up to 32 slots, run that task with one
+ * photon per lane, push each photon to its next queue.  Any 32 photons of the pool that wait for the same kind of work
+ * form a full warp, so the lanes stay busy whatever the photons' histories; no CTA barrier is needed after start-up.
+ * The device functions (segment_solve, refl_geometry*, fresnel_rtot*, source_sample) are the ones pcb_trace.cuh uses:
+ * results are identical photon by photon (tests/test_gpu_parity.py runs both kernels).
+ */
+#ifndef PCB_TRACE2_CUH
+#define PCB_TRACE2_CUH
+
+#include "pcb_trace.cuh"
+
+#ifndef T2_THREADS
+#define T2_THREADS 640
+#endif
+#ifndef T2_NP
+#define T2_NP 1152 /* photon slots per CTA */
+#endif
+#define T2_QCAP 2048 /* ring capacity, power of two > T2_NP */
+#define T2_EMPTY 0xFFFFu
+
+enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_DONE, TQ_N };
+
+/* flag bits of a photon slot */
+enum { F_SLOW = 1, F_DEEP = 2, F_WINIT = 4, F_INCUR = 8, F_INNXT = 16 };
+
+struct T2Dbl { /* the 16 double fields of the pool: ex ey ez dx dy dz vx vy vz lhx lhy lhz dtrav A B aux, each [T2_NP] */
+	double *base;
+	__device__ __forceinline__ double *operator[](int k) const { return base + k * T2_NP; }
+};
+struct T2Shared { /* pointers into dynamic shared memory */
+	T2Dbl d;
+	unsigned *lid;
+	int *irefl, *ix, *iseg, *ntrace;
+	unsigned char *flags;
+	signed char *code;
+	volatile unsigned short *q[TQ_N];
+};
+
+enum { D_EX = 0, D_EY, D_EZ, D_DX, D_DY, D_DZ, D_VX, D_VY, D_VZ, D_LHX, D_LHY, D_LHZ, D_DTRAV, D_A, D_B, D_AUX, D_N };
+
+__device__ __forceinline__ void t2_push(volatile unsigned short *buf, unsigned *tail, unsigned slot)
+{
+	__threadfence_block(); /* the slot's state is visible before its id is */
+	const unsigned t = atomicAdd(tail, 1u) & (T2_QCAP - 1);
+	while (buf[t] != T2_EMPTY) {
+	}
+	buf[t] = (unsigned short)slot;
+}
+
+template <int MODE, int EXACT_W>
+__global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTraceParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ __align__(8) uint64_t tma_bar;
+	__shared__ unsigned q_head[TQ_N], q_tail[TQ_N];
+	__shared__ int live;
+
+	const PcbOptic &o = P.o;
+	const int nmax = o.nmax;
+	const int nE = o.n_energies;
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+
+	/* ---- carve shared memory: tables | photon state | queues | Fresnel staging ---- */
+	const uint32_t tb = (uint32_t)o.tstride * 8u;
+	unsigned char *p = smem_raw;
+	Tables T;
+	T.z = reinterpret_cast<double *>(p); /* the three tables of the segment scan are staged; cap/ext (one read per wall hit) stay global */
+	T.hexz = reinterpret_cast<double *>(p + tb);
+	T.rm = reinterpret_cast<double *>(p + 2 * tb);
+	T.cap = o.cap;
+	T.ext = o.ext;
+	p += 3 * tb;
+	T2Shared S;
+	S.d.base = reinterpret_cast<double *>(p);
+	p += D_N * T2_NP * 8;
+	S.lid = reinterpret_cast<unsigned *>(p); p += T2_NP * 4;
+	S.irefl = reinterpret_cast<int *>(p); p += T2_NP * 4;
+	S.ix = reinterpret_cast<int *>(p); p += T2_NP * 4;
+	S.iseg = reinterpret_cast<int *>(p); p += T2_NP * 4;
+	S.ntrace = reinterpret_cast<int *>(p); p += T2_NP * 4;
+	for (int k = 0; k < TQ_N; k++) {
+		S.q[k] = reinterpret_cast<volatile unsigned short *>(p);
+		p += T2_QCAP * 2;
+	}
+	unsigned short *batch = reinterpret_cast<unsigned short *>(p) + warp * 32; /* slots of this warp's current batch */
+	p += (T2_THREADS / 32) * 32 * 2;
+	S.flags = p; p += T2_NP;
+	S.code = reinterpret_cast<signed char *>(p); p += T2_NP;
+
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tma_bar)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int i = threadIdx.x; i < TQ_N * T2_QCAP; i += blockDim.x)
+		S.q[i / T2_QCAP][i % T2_QCAP] = T2_EMPTY;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tma_bar)), "r"(3 * tb) : "memory");
+		tma_bulk_load(const_cast<double *>(T.z), o.z, tb, &tma_bar);
+		tma_bulk_load(const_cast<double *>(T.hexz), o.hexz, tb, &tma_bar);
+		tma_bulk_load(const_cast<double *>(T.rm), o.rm, tb, &tma_bar);
+		for (int k = 0; k < TQ_N; k++) {
+			q_head[k] = 0;
+			q_tail[k] = 0;
+		}
+		q_tail[TQ_NEW] = T2_NP; /* every slot starts free */
+		live = T2_NP;
+	}
+	for (int i = threadIdx.x; i < T2_NP; i += blockDim.x)
+		S.q[TQ_NEW][i] = (unsigned short)i;
+	{
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+				     : "=r"(done)
+				     : "r"(smem_u32(&tma_bar))
+				     : "memory");
+		}
+	}
+	__syncthreads();
+
+	const double *ec = o.ec;
+	double *wcta = P.wscratch + (unsigned long long)blockIdx.x * T2_NP * (unsigned long long)nE; /* weight vector of slot s at wcta + s*nE */
+	unsigned int c_steps = 0, c_solves = 0, c_refl = 0, c_launch = 0;
+	unsigned int s_batches = 0, s_lanes = 0, s_empty = 0, s_lost = 0, s_hit_b = 0, s_hit_l = 0, s_scan_b = 0, s_scan_l = 0;
+	volatile unsigned *vhead = q_head, *vtail = q_tail;
+	volatile int *vlive = &live;
+
+	/* begin one capil_trace call for the photon in registers (capil.c:1236-1246); see pcb_trace.cuh::trace_begin */
+#define T2_TRACE_BEGIN(on_wall)                                                                                       \
+	do {                                                                                                          \
+		if (ntrace > nmax) {                                                                                  \
+			code = 1;                                                                                     \
+			next = TQ_DONE;                                                                               \
+		} else {                                                                                              \
+			ntrace++;                                                                                     \
+			V3 d_ = {dx, dy, dz};                                                                         \
+			norm3(d_);                                                                                    \
+			dx = d_.x; dy = d_.y; dz = d_.z;                                                              \
+			lhx = ex; lhy = ey; lhz = ez;                                                                 \
+			iseg = ix;                                                                                    \
+			flags &= ~F_INCUR;                                                                            \
+			if (iseg < nmax) {                                                                            \
+				const bool steep_ = (dx * dx + dy * dy) > ((flags & F_DEEP) ? 0.0625 : 1.e-4) * (dz * dz); \
+				bool in_;                                                                             \
+				if ((on_wall) && !steep_) {                                                           \
+					in_ = true;                                                                   \
+				} else {                                                                              \
+					const double t_ = (T.z[iseg] - ez) * (1.0 / dz);                              \
+					const double hz_ = T.hexz[iseg];                                              \
+					const double ux_ = pcb_fma(-A, hz_, pcb_fma(dx, t_, ex));                     \
+					const double uy_ = pcb_fma(-B, hz_, pcb_fma(dy, t_, ey));                     \
+					in_ = pcb_fma(ux_, ux_, uy_ * uy_) < T.rm[iseg];                              \
+				}                                                                                     \
+				if (in_)                                                                              \
+					flags |= F_INCUR;                                                             \
+			}                                                                                             \
+			next = TQ_SCAN;                                                                               \
+		}                                                                                                     \
+	} while (0)
+
+	/* segment scan of the photon in registers: up to K steps with the convexity skip test (see pcb_trace.cuh, phase SCAN).
+	 * Leaves next = TQ_HIT (candidate segment found), TQ_DONE (flew out of the end) or TQ_SCAN (budget used up). */
+#define T2_SCAN_STEPS(K)                                                                                               \
+	do {                                                                                                          \
+		const double inv_dz_ = 1.0 / dz;                                                                      \
+		bool in_cur_ = flags & F_INCUR;                                                                       \
+		const bool slow_ = flags & F_SLOW;                                                                    \
+		next = TQ_SCAN;                                                                                       \
+		_Pragma("unroll 1") for (int rep_ = 0; rep_ < (K); rep_++)                                            \
+		{                                                                                                     \
+			if (iseg >= nmax) { /* capil.c:1312-1313 -> -2 -> launch returns 1 */                         \
+				code = 1;                                                                             \
+				next = TQ_DONE;                                                                       \
+				break;                                                                                \
+			}                                                                                             \
+			const double t_ = (T.z[iseg + 1] - ez) * inv_dz_;                                             \
+			const double hz_ = T.hexz[iseg + 1];                                                          \
+			const double ux_ = pcb_fma(-A, hz_, pcb_fma(dx, t_, ex));                                     \
+			const double uy_ = pcb_fma(-B, hz_, pcb_fma(dy, t_, ey));                                     \
+			const bool in_next_ = pcb_fma(ux_, ux_, uy_ * uy_) < T.rm[iseg + 1];                          \
+			if (in_cur_ && in_next_ && !slow_) {                                                          \
+				iseg++;                                                                               \
+				c_steps++;                                                                            \
+				in_cur_ = in_next_;                                                                   \
+			} else {                                                                                      \
+				flags = (flags & ~F_INNXT) | (in_next_ ? F_INNXT : 0);                                \
+				next = TQ_HIT;                                                                        \
+				break;                                                                                \
+			}                                                                                             \
+		}                                                                                                     \
+		flags = (flags & ~F_INCUR) | (in_cur_ ? F_INCUR : 0);                                                 \
+	} while (0)
+
+	for (;;) {
+		/* ---------------- claim a batch: lane k polls queue k, the fullest-first rule is evaluated by ballot ---------------- */
+		int type = -1, n = 0;
+		unsigned base = 0;
+		{
+			unsigned cnt = 0;
+			if (lane < TQ_N)
+				cnt = vtail[lane] - vhead[lane];
+			/* priority: a full batch of wall hits, then of finished photons, long scans, free slots; else whatever is fullest */
+			const unsigned full = __ballot_sync(0xffffffffu, cnt >= 32u);
+			const unsigned any = __ballot_sync(0xffffffffu, cnt > 0u);
+			/* a full batch of wall hits first (then long scans, finished photons, free slots); without any full batch, recycle
+			 * slots first (DONE, NEW: cheap, and they put more photons in flight) and take a partial HIT batch last */
+			const int order_full[TQ_N] = {TQ_HIT, TQ_SCAN, TQ_DONE, TQ_NEW};
+			const int order_any[TQ_N] = {TQ_DONE, TQ_NEW, TQ_SCAN, TQ_HIT};
+			const unsigned pick = full ? full : any;
+			if (pick) {
+#pragma unroll
+				for (int k = TQ_N - 1; k >= 0; k--) {
+					const int qk = full ? order_full[k] : order_any[k];
+					if (pick & (1u << qk))
+						type = qk;
+				}
+				if (lane == 0) {
+					const unsigned h = vhead[type];
+					const unsigned avail = vtail[type] - h;
+					const unsigned want = avail < 32u ? avail : 32u;
+					if (want == 0 || atomicCAS(&q_head[type], h, h + want) != h)
+						n = 0;
+					else {
+						n = (int)want;
+						base = h;
+					}
+				}
+				n = __shfl_sync(0xffffffffu, n, 0);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (n == 0) {
+					s_lost++;
+					continue; /* lost the race */
+				}
+			} else {
+				if (*vlive == 0)
+					break; /* nothing queued, nothing in flight */
+				s_empty++;
+				__nanosleep(400);
+				continue;
+			}
+		}
+		s_batches++;
+		s_lanes += n;
+		if (type == TQ_HIT) { s_hit_b++; s_hit_l += n; }
+		if (type == TQ_SCAN) { s_scan_b++; s_scan_l += n; }
+		const bool act = lane < n;
+		unsigned slot = 0;
+		if (act) {
+			volatile unsigned short *e = &S.q[type][(base + lane) & (T2_QCAP - 1)];
+			unsigned short v;
+			while ((v = *e) == T2_EMPTY) {
+			}
+			*e = T2_EMPTY;
+			slot = v;
+		}
+		__threadfence_block();
+
+		/* ---------------- photon state: shared memory -> registers ---------------- */
+		double ex = 0, ey = 0, ez = 0, dx = 0, dy = 0, dz = 1, vx = 0, vy = 0, vz = 0, lhx = 0, lhy = 0, lhz = 0, snx = 0, sny = 0, snz = 0;
+		double cosalfa = 0, dtrav = 0, A = 0, B = 0;
+		unsigned lid = 0;
+		int irefl = 0, ix = 0, iseg = 0, ntrace = 0, code = 0;
+		unsigned flags = 0;
+		if (act && type != TQ_NEW) {
+			ex = S.d[D_EX][slot]; ey = S.d[D_EY][slot]; ez = S.d[D_EZ][slot];
+			dx = S.d[D_DX][slot]; dy = S.d[D_DY][slot]; dz = S.d[D_DZ][slot];
+			A = S.d[D_A][slot]; B = S.d[D_B][slot];
+			iseg = S.iseg[slot];
+			flags = S.flags[slot];
+			if (type != TQ_SCAN) {
+				lhx = S.d[D_LHX][slot]; lhy = S.d[D_LHY][slot]; lhz = S.d[D_LHZ][slot];
+				vx = S.d[D_VX][slot]; vy = S.d[D_VY][slot]; vz = S.d[D_VZ][slot];
+				dtrav = S.d[D_DTRAV][slot];
+				ix = S.ix[slot];
+				lid = S.lid[slot]; irefl = S.irefl[slot]; ntrace = S.ntrace[slot]; code = S.code[slot];
+			}
+		}
+		int next = -1; /* queue the photon goes to; -1: slot retired */
+
+		if (type == TQ_SCAN) {
+			/* ---------------- SCAN: continuation of a long free flight ---------------- */
+			if (act) {
+				T2_SCAN_STEPS(64);
+				S.iseg[slot] = iseg;
+				S.flags[slot] = (unsigned char)flags;
+				if (next == TQ_DONE)
+					S.code[slot] = (signed char)code;
+			}
+		} else if (type == TQ_HIT) {
+			/* ---------------- HIT: solve the candidate segment (capil.c:1256-1309); on a hit the reflection: travel and in-optic
+			 * checks (capil.c:1315-1343), capil_reflect preamble + geometry, the energy loop over the batch's (photon, energy)
+			 * pairs, the specular direction and the start of the next capil_trace call; then scan on to the next candidate ---------------- */
+			bool hitting = false;
+			double alfa = 0;
+			if (act) {
+				const bool slow = flags & F_SLOW;
+				const int i = iseg;
+				c_steps++;
+				c_solves++;
+				const double z0 = T.z[i], z1 = T.z[i + 1];
+				V3 c0 = {A * T.hexz[i], B * T.hexz[i], z0};
+				V3 c1 = {A * T.hexz[i + 1], B * T.hexz[i + 1], z1};
+				V3 p0 = {ex + dx * (z0 - ez) / dz, ey + dy * (z0 - ez) / dz, z0};
+				const double cap0 = __ldg(T.cap + i), cap1 = __ldg(T.cap + i + 1);
+				if (slow && (within_pc(__ldg(T.ext + i), c0.x, c0.y) == 0 || within_pc(__ldg(T.ext + i + 1), c1.x, c1.y) == 0)) { /* capil.c:1263-1266 */
+					code = -1;
+					next = TQ_DONE;
+				} else {
+					V3 hit = {lhx, lhy, lhz}, sn;
+					V3 pd = {dx, dy, dz};
+					int iesc;
+					if (z0 < 0. || z1 < 0 || cap0 < 0. || cap1 < 0. || dz < 0 || z1 <= z0) {
+						iesc = -1;
+						sn.x = sn.y = sn.z = 0.0;
+					} else {
+						iesc = segment_solve(c0, c1, cap0, cap1, p0, pd, lhz, hit, sn);
+					}
+					const double ca = dot3(sn, pd);
+					if (iesc == 1) {
+						const double ac = acos(ca);
+						if (ac > PCB_PI / 2. || ac < 0.)
+							iesc = -5;
+						lhx = hit.x; lhy = hit.y; lhz = hit.z;
+					}
+					if (iesc == 1) {
+						bool outside = false;
+						if (slow) {
+							const double e0 = __ldg(T.ext + i), e1 = __ldg(T.ext + i + 1);
+							const double ext_here = ((e0 - e1) / (z0 - z1)) * (hit.z - z1) + e1;
+							outside = o.mono ? (sqrt(hit.x * hit.x + hit.y * hit.y) >= ext_here) : (within_pc(ext_here, hit.x, hit.y) == 0);
+						}
+						if (outside) {
+							code = -1;
+							next = TQ_DONE;
+						} else {
+							ix = i + 1;
+							snx = sn.x; sny = sn.y; snz = sn.z;
+							cosalfa = ca;
+							hitting = true;
+						}
+					} else {
+						bool outside = false;
+						if (slow || !(flags & F_INCUR))
+							outside = (within_pc(__ldg(T.ext + i), p0.x, p0.y) == 0);
+						if (outside) {
+							code = -1;
+							next = TQ_DONE;
+						} else {
+							iseg = i + 1;
+							flags = (flags & ~F_INCUR) | ((flags & F_INNXT) ? F_INCUR : 0);
+							next = TQ_SCAN;
+						}
+					}
+				}
+				if (hitting) {
+					c_refl++;
+					const double rx = lhx - ex, ry = lhy - ey, rz = lhz - ez;
+					dtrav += sqrt(rx * rx + ry * ry + rz * rz); /* capil.c:1315-1319 */
+					ex = lhx; ey = lhy; ez = lhz;
+					if (fabs(cosalfa) > 1.0) {
+						code = -1;
+						next = TQ_DONE;
+						hitting = false;
+					}
+				}
+				if (hitting) { /* *ix = last i < nmax with z[i] <= hit z (capil.c:1330-1333) */
+					int found = -1;
+					if (ix < nmax && T.z[ix] <= ez) {
+						found = ix;
+					} else {
+						for (int j = ix - 1; j >= 0; j--)
+							if (T.z[j] <= ez) {
+								found = j;
+								break;
+							}
+					}
+					if (found >= 0)
+						ix = found;
+					if (slow) { /* capil.c:1334-1343 */
+						const double e0 = __ldg(T.ext + ix), e1 = __ldg(T.ext + ix + 1);
+						const double ext_here = ((e1 - e0) / (T.z[ix + 1] - T.z[ix])) * (lhz - T.z[ix]) + e0;
+						const bool outside = o.mono ? (ex * ex + ey * ey >= ext_here) : (within_pc(ext_here, ex, ey) == 0);
+						if (outside) {
+							code = -1;
+							next = TQ_DONE;
+							hitting = false;
+						}
+					}
+				}
+				if (hitting) { /* capil_reflect preamble, capil.c:596-602, and the energy-independent geometry */
+					V3 sn = {snx, sny, snz};
+					norm3(sn);
+					V3 d = {dx, dy, dz};
+					norm3(d);
+					dx = d.x; dy = d.y; dz = d.z;
+					alfa = dot3(d, sn);
+					if (alfa < 0.) {
+						code = -1;
+						next = TQ_DONE;
+						hitting = false;
+					} else {
+						V3 ev = {vx, vy, vz};
+						ReflGeom g;
+						if (EXACT_W)
+							refl_geometry(sn, d, ev, g);
+						else
+							refl_geometry_fast(sn, d, ev, g);
+						vx = g.new_ev.x; vy = g.new_ev.y; vz = g.new_ev.z;
+						/* geometry for the pair loop, readable by every lane: the slot's photon_coord fields (free until the
+						 * next trace call) and aux */
+						S.d[D_LHX][slot] = g.cos_t; S.d[D_LHY][slot] = g.sin_t; S.d[D_LHZ][slot] = g.frac_s;
+						S.d[D_AUX][slot] = alfa;
+					}
+				}
+			}
+			/* ---- energy loop (capil.c:625-645) over the reflecting photons of the batch ---- */
+			const unsigned go = __ballot_sync(0xffffffffu, hitting);
+			const int n_go = __popc(go);
+			if (hitting) {
+				batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
+				if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
+					double *w0 = wcta + (unsigned long long)slot * nE;
+					for (int e2 = 0; e2 < nE; e2++)
+						w0[e2] = 1.0;
+				}
+			}
+			__syncwarp();
+			const int total = n_go * nE;
+			const bool rough = (o.sig_rough != 0.0);
+			const double sig_rough = o.sig_rough;
+			unsigned alive_bits = 0, bad_bits = 0; /* bit k: k-th reflecting photon of the batch */
+			int pi = lane / nE, e = lane - pi * nE;
+			const int dpi = 32 / nE, de = 32 - dpi * nE;
+			int j0 = 0;
+			if (!EXACT_W) {
+				enum { U = 2 };
+				int pu[U], eu[U];
+				pu[0] = pi; eu[0] = e;
+#pragma unroll
+				for (int u = 1; u < U; u++) {
+					pu[u] = pu[u - 1] + dpi; eu[u] = eu[u - 1] + de;
+					if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
+				}
+				const int dpiU = (32 * U) / nE, deU = 32 * U - dpiU * nE;
+				for (; j0 + 32 * U <= total; j0 += 32 * U) {
+					unsigned sl[U];
+					double *wp[U];
+					double w[U], r[U];
+#pragma unroll
+					for (int u = 0; u < U; u++) {
+						sl[u] = batch[pu[u]];
+						wp[u] = wcta + (unsigned long long)sl[u] * nE + eu[u];
+						w[u] = *wp[u];
+					}
+#pragma unroll
+					for (int u = 0; u < U; u++)
+						r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
+									 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_LHX][sl[u]], S.d[D_LHY][sl[u]], S.d[D_LHZ][sl[u]],
+									 1. - S.d[D_LHZ][sl[u]]);
+#pragma unroll
+					for (int u = 0; u < U; u++) {
+						if (rough) {
+							const double cr = __ldg(ec + EC_KR * nE + eu[u]) * S.d[D_AUX][sl[u]] * sig_rough;
+							w[u] = w[u] * r[u] * exp(-1. * cr * cr);
+						} else {
+							w[u] = w[u] * r[u] * 1.0;
+						}
+						*wp[u] = w[u];
+						if (r[u] < 0. || r[u] > 1.)
+							bad_bits |= 1u << pu[u];
+						if (w[u] >= 1.e-4)
+							alive_bits |= 1u << pu[u];
+						pu[u] += dpiU; eu[u] += deU;
+						if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
+					}
+				}
+				pi = pu[0];
+				e = eu[0];
+			}
+			for (; j0 < total; j0 += 32) {
+				if (j0 + lane < total) {
+					const unsigned sl = batch[pi];
+					double *wp = wcta + (unsigned long long)sl * nE + e;
+					double w = *wp;
+					const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
+					const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
+					const double c_t = S.d[D_LHX][sl], s_t = S.d[D_LHY][sl], f_s = S.d[D_LHZ][sl];
+					const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s)
+								    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s);
+					if (rough) {
+						const double cons1 = __ldg(ec + EC_KR * nE + e) * S.d[D_AUX][sl] * sig_rough;
+						w = w * rtot * exp(-1. * cons1 * cons1);
+					} else {
+						w = w * rtot * 1.0;
+					}
+					*wp = w;
+					if (rtot < 0. || rtot > 1.)
+						bad_bits |= 1u << pi;
+					if (w >= 1.e-4)
+						alive_bits |= 1u << pi;
+				}
+				pi += dpi;
+				e += de;
+				if (e >= nE) {
+					e -= nE;
+					pi++;
+				}
+			}
+			alive_bits = __reduce_or_sync(0xffffffffu, alive_bits);
+			bad_bits = __reduce_or_sync(0xffffffffu, bad_bits);
+			if (hitting) {
+				const int rank = __popc(go & ((1u << lane) - 1u));
+				flags |= F_WINIT;
+				if ((bad_bits >> rank) & 1u) {
+					code = -1;
+					next = TQ_DONE;
+				} else if ((alive_bits >> rank) & 1u) { /* capil.c:1346-1352 */
+					dx = dx - 2.0 * cosalfa * snx;
+					dy = dy - 2.0 * cosalfa * sny;
+					dz = dz - 2.0 * cosalfa * snz;
+					V3 d = {dx, dy, dz};
+					norm3(d);
+					dx = d.x; dy = d.y; dz = d.z;
+					irefl++;
+					T2_TRACE_BEGIN(true);
+				} else {
+					code = 0;
+					next = TQ_DONE;
+				}
+			}
+			if (act) {
+				if (next == TQ_SCAN) /* on to the next candidate segment while the photon is in registers */
+					T2_SCAN_STEPS(24);
+				S.d[D_EX][slot] = ex; S.d[D_EY][slot] = ey; S.d[D_EZ][slot] = ez;
+				S.d[D_DX][slot] = dx; S.d[D_DY][slot] = dy; S.d[D_DZ][slot] = dz;
+				S.d[D_VX][slot] = vx; S.d[D_VY][slot] = vy; S.d[D_VZ][slot] = vz;
+				S.d[D_LHX][slot] = lhx; S.d[D_LHY][slot] = lhy; S.d[D_LHZ][slot] = lhz;
+				S.d[D_DTRAV][slot] = dtrav;
+				S.iseg[slot] = iseg; S.ix[slot] = ix; S.irefl[slot] = irefl; S.ntrace[slot] = ntrace;
+				S.flags[slot] = (unsigned char)flags;
+				S.code[slot] = (signed char)code;
+			}
+			__syncwarp();
+		} else if (type == TQ_DONE) {
+			/* ---------------- DONE: classify (source.c:758-777), dense per-id outputs ---------------- */
+			if (act) {
+				const unsigned long long nn = P.n_ids;
+				const double *wsl = wcta + (unsigned long long)slot * nE;
+				const bool w_init = flags & F_WINIT;
+				int status = code;
+				const double zt = T.z[nmax];
+				const double ext_end = __ldg(T.ext + nmax);
+				if (MODE == MODE_SOURCE && code == 1) {
+					const double px = ex + dx * (zt - ez) / dz;
+					const double py = ey + dy * (zt - ez) / dz;
+					const int inside = o.mono ? ((sqrt((px) * (px) + (py) * (py)) > ext_end) ? 0 : 1) : within_pc(ext_end, px, py);
+					if (inside != 1)
+						status = ST_MISSED_WINDOW;
+				}
+				P.out.status[lid] = (int8_t)status;
+				P.out.irefl[lid] = irefl;
+				double *F = P.out.fields;
+				const bool wr_rec = (MODE == MODE_REPLAY) || status == ST_EXIT || P.record_all;
+				if (MODE == MODE_REPLAY) {
+					F[0 * nn + lid] = ex; F[1 * nn + lid] = ey; F[2 * nn + lid] = ez;
+					F[3 * nn + lid] = dx; F[4 * nn + lid] = dy; F[5 * nn + lid] = dz;
+					F[6 * nn + lid] = vx; F[7 * nn + lid] = vy; F[8 * nn + lid] = vz;
+					F[9 * nn + lid] = dtrav;
+					F[10 * nn + lid] = (double)ntrace;
+				} else if (wr_rec) {
+					StartState s0;
+					source_sample(P.s, o.mono, P.id0 + lid, s0);
+					V3 sd = s0.dir;
+					for (int k = 0; k < ntrace + 1; k++) {
+						V3 prev = sd;
+						norm3(sd);
+						if (sd.x == prev.x && sd.y == prev.y && sd.z == prev.z)
+							break;
+					}
+					F[0 * nn + lid] = s0.src_x; F[1 * nn + lid] = s0.src_y;
+					F[2 * nn + lid] = s0.coords.x; F[3 * nn + lid] = s0.coords.y;
+					F[4 * nn + lid] = sd.x; F[5 * nn + lid] = sd.y;
+					const double ca = dot3(s0.ev, sd);
+					const double al = acos(ca);
+					const double c_ae = 1. / sin(al), c_be = -1. * c_ae * ca;
+					V3 t = {s0.ev.x * c_ae + sd.x * c_be, s0.ev.y * c_ae + sd.y * c_be, s0.ev.z * c_ae + sd.z * c_be};
+					norm3(t);
+					F[6 * nn + lid] = round(t.x); F[7 * nn + lid] = round(t.y);
+					const double px = ex + dx * (zt - ez) / dz;
+					const double py = ey + dy * (zt - ez) / dz;
+					const double pz = ez + dz * (zt - ez) / dz;
+					F[8 * nn + lid] = px; F[9 * nn + lid] = py; F[10 * nn + lid] = pz;
+					F[11 * nn + lid] = dx; F[12 * nn + lid] = dy;
+					V3 u = {vx * c_ae + dx * c_be, vy * c_ae + dy * c_be, vz * c_ae + dz * c_be};
+					norm3(u);
+					F[13 * nn + lid] = round(u.x); F[14 * nn + lid] = round(u.y);
+					F[15 * nn + lid] = (double)irefl;
+					F[16 * nn + lid] = dtrav + sqrt((px - ex) * (px - ex) + (py - ey) * (py - ey) + (zt - ez) * (zt - ez));
+				}
+				if (wr_rec || status == ST_ABSORBED) {
+					double *W = P.out.weights + (unsigned long long)lid * nE;
+					for (int e2 = 0; e2 < nE; e2++)
+						W[e2] = w_init ? wsl[e2] : 1.0;
+				}
+				next = TQ_NEW;
+			}
+		} else {
+			/* ---------------- NEW: fetch an id, build the start state, launch (photon.c:476-645) ---------------- */
+			const unsigned m = __ballot_sync(0xffffffffu, act);
+			unsigned long long idbase = 0;
+			if (m) {
+				const int leader = __ffs(m) - 1;
+				if (lane == leader)
+					idbase = atomicAdd(&P.wc->next_id, (unsigned long long)__popc(m));
+				idbase = __shfl_sync(0xffffffffu, idbase, leader);
+			}
+			if (act) {
+				const unsigned long long id = idbase + __popc(m & ((1u << lane) - 1u));
+				if (id >= P.n_ids) {
+					atomicSub(&live, 1); /* no ids left: the slot retires */
+					next = -1;
+				} else {
+					lid = (unsigned)id;
+					c_launch++;
+					StartState s0;
+					if (MODE == MODE_SOURCE) {
+						source_sample(P.s, o.mono, P.id0 + id, s0);
+					} else {
+						s0.coords.x = P.rin.coords[3 * id]; s0.coords.y = P.rin.coords[3 * id + 1]; s0.coords.z = P.rin.coords[3 * id + 2];
+						s0.dir.x = P.rin.dir[3 * id]; s0.dir.y = P.rin.dir[3 * id + 1]; s0.dir.z = P.rin.dir[3 * id + 2];
+						s0.ev.x = P.rin.ev[3 * id]; s0.ev.y = P.rin.ev[3 * id + 1]; s0.ev.z = P.rin.ev[3 * id + 2];
+					}
+					irefl = 0; ntrace = 0; dtrav = 0; code = 0; flags = 0;
+					norm3(s0.dir);
+					ex = s0.coords.x; ey = s0.coords.y; ez = s0.coords.z;
+					V3 d = s0.dir;
+					norm3(d);
+					dx = d.x; dy = d.y; dz = d.z;
+					vx = s0.ev.x; vy = s0.ev.y; vz = s0.ev.z;
+					int z_id = 0;
+					if (ez > 0) {
+						for (int i = 0; i < nmax; i++)
+							if (T.z[i] <= ez)
+								z_id = i;
+					}
+					const double ext0 = __ldg(T.ext + z_id), ext1 = __ldg(T.ext + z_id + 1);
+					const double ext_here = ((ext0 - ext1) / (T.z[z_id] - T.z[z_id + 1])) * (ez - T.z[z_id]) + ext0;
+					double q_i = 0, r_i = 0;
+					bool outside;
+					if (o.mono) {
+						outside = (sqrt((ex) * (ex) + (ey) * (ey)) > ext_here);
+					} else {
+						const double hz = ext_here / (2. * PCB_COSPI_6 * (o.n_shells + 1));
+						hex_cell(hz, ex, ey, q_i, r_i);
+						outside = (within_pc(ext_here, ex, ey) == 0);
+					}
+					if (outside) {
+						code = -2;
+						next = TQ_DONE;
+					} else {
+						A = (2. * q_i + r_i) * PCB_COSPI_6;
+						B = r_i * (3. / 2);
+						ix = 0;
+						if (ez > 0) {
+							for (int i = 0; i <= nmax; i++)
+								if (T.z[i] <= ez)
+									ix = i;
+						} else if (T.z[0] <= ez) {
+							ix = 0;
+							for (int i = 1; i <= nmax && T.z[i] <= ez; i++)
+								ix = i;
+						}
+						double rad_here, cx_here, cy_here;
+						if (ez > 0) {
+							const double dzs = (T.z[z_id + 1] - T.z[z_id]), off = (ez - T.z[z_id]);
+							const double cx0 = A * T.hexz[z_id], cx1 = A * T.hexz[z_id + 1];
+							const double cy0 = B * T.hexz[z_id], cy1 = B * T.hexz[z_id + 1];
+							const double cp0 = __ldg(T.cap + z_id), cp1 = __ldg(T.cap + z_id + 1);
+							rad_here = ((cp1 - cp0) / dzs) * off + cp0;
+							cx_here = ((cx1 - cx0) / dzs) * off + cx0;
+							cy_here = ((cy1 - cy0) / dzs) * off + cy0;
+						} else {
+							rad_here = __ldg(T.cap);
+							cx_here = A * T.hexz[0];
+							cy_here = B * T.hexz[0];
+						}
+						const double d_axis = sqrt((ex - cx_here) * (ex - cx_here) + (ey - cy_here) * (ey - cy_here));
+						if (d_axis > rad_here) {
+							code = 2;
+							next = TQ_DONE;
+						} else {
+							const double m1 = fabs(B), m2 = fabs(PCB_COSPI_6 * A + 0.5 * B), m3 = fabs(PCB_COSPI_6 * A - 0.5 * B);
+							const double mm = fmax(m1, fmax(m2, m3));
+							if (o.all_slow || !(mm < o.m_safe))
+								flags |= F_SLOW;
+							if (mm < o.m_deep)
+								flags |= F_DEEP;
+							T2_TRACE_BEGIN(false);
+							if (next == TQ_SCAN)
+								T2_SCAN_STEPS(24);
+						}
+					}
+					S.d[D_EX][slot] = ex; S.d[D_EY][slot] = ey; S.d[D_EZ][slot] = ez;
+					S.d[D_DX][slot] = dx; S.d[D_DY][slot] = dy; S.d[D_DZ][slot] = dz;
+					S.d[D_VX][slot] = vx; S.d[D_VY][slot] = vy; S.d[D_VZ][slot] = vz;
+					S.d[D_LHX][slot] = lhx; S.d[D_LHY][slot] = lhy; S.d[D_LHZ][slot] = lhz;
+					S.d[D_DTRAV][slot] = dtrav; S.d[D_A][slot] = A; S.d[D_B][slot] = B;
+					S.lid[slot] = lid; S.irefl[slot] = irefl; S.ix[slot] = ix; S.iseg[slot] = iseg; S.ntrace[slot] = ntrace;
+					S.flags[slot] = (unsigned char)flags;
+					S.code[slot] = (signed char)code;
+				}
+			}
+		}
+
+		/* ---------------- hand the photons on ---------------- */
+		if (act && next >= 0)
+			t2_push(S.q[next], &q_tail[next], slot);
+	}
+#undef T2_SCAN_STEPS
+#undef T2_TRACE_BEGIN
+
+	for (int off = 16; off > 0; off >>= 1) {
+		c_steps += __shfl_down_sync(0xffffffffu, c_steps, off);
+		c_solves += __shfl_down_sync(0xffffffffu, c_solves, off);
+		c_refl += __shfl_down_sync(0xffffffffu, c_refl, off);
+		c_launch += __shfl_down_sync(0xffffffffu, c_launch, off);
+	}
+	if (lane == 0) {
+		atomicAdd(&P.wc->seg_steps, (unsigned long long)c_steps);
+		atomicAdd(&P.wc->solves, (unsigned long long)c_solves);
+		atomicAdd(&P.wc->reflections, (unsigned long long)c_refl);
+		atomicAdd(&P.wc->launched, (unsigned long long)c_launch);
+		atomicAdd(&P.wc->dbg[0], (unsigned long long)s_batches);
+		atomicAdd(&P.wc->dbg[1], (unsigned long long)s_lanes);
+		atomicAdd(&P.wc->dbg[2], (unsigned long long)s_empty);
+		atomicAdd(&P.wc->dbg[3], (unsigned long long)s_lost);
+		atomicAdd(&P.wc->dbg[4], (unsigned long long)s_hit_b);
+		atomicAdd(&P.wc->dbg[5], (unsigned long long)s_hit_l);
+		atomicAdd(&P.wc->dbg[6], (unsigned long long)s_scan_b);
+		atomicAdd(&P.wc->dbg[7], (unsigned long long)s_scan_l);
+	}
+}
+
+/* dynamic shared memory of pcb_trace2_kernel for a table stride of `tstride` doubles */
+static inline size_t t2_smem_bytes(int tstride)
+{
+	return 3 * (size_t)tstride * 8 + 16 * (size_t)T2_NP * 8 + (size_t)(T2_THREADS / 32) * 32 * 2 + 5 * (size_t)T2_NP * 4 + (size_t)TQ_N * T2_QCAP * 2 +
+	       2 * (size_t)T2_NP + 64;
+}
+
+#endif
