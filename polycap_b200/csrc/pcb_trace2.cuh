@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		flags = (flags & ~F_INCUR) | (in_cur_ ? F_INCUR : 0);                                                 \
 	} while (0)
 
+	unsigned backoff = 256u;
 	for (;;) {
 		/* ---------------- claim a batch: lane k polls queue k, the fullest-first rule is evaluated by ballot ---------------- */
 		int type = -1, n = 0;
@@ -253,10 +254,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				if (*vlive == 0)
 					break; /* nothing queued, nothing in flight */
 				s_empty++;
-				__nanosleep(400);
+				__nanosleep(backoff); /* all photons are in other warps' hands: back off so the pollers leave the issue slots alone */
+				if (backoff < 4096u)
+					backoff <<= 1;
 				continue;
 			}
 		}
+		backoff = 256u;
 		s_batches++;
 		s_lanes += n;
 		if (type == TQ_HIT) { s_hit_b++; s_hit_l += n; }
