@@ -51,3 +51,16 @@ def test_reference_source_program(tmp_path):
         return
     # the only accepted stop: the HDF5 write assertion, after all efficiency / record assertions passed
     assert "source.c:298" in r.stderr and "write_hdf5" in r.stderr, r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_reference_cli(tmp_path):
+    """the reference's CLI (src/main.c, unmodified): `polycap input.inp out.h5` -- 30000 exit photons, 291 energies, HDF5 output"""
+    exe = os.path.join(BIN, "b200_polycap")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/b200_polycap not built (make -C oracle b200-tests)")
+    (tmp_path / "ellip_l9.inp").write_text(ELLIP_INP)
+    r = subprocess.run([exe, "ellip_l9.inp", "out.h5"], cwd=tmp_path, env=dict(os.environ, POLYCAP_B200_QUIET="1"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Average number of reflections" in r.stdout and "iexit: 30000" in r.stdout  # the CLI hard-codes 30000 photons (src/main.c:32)
+    assert (tmp_path / "out.h5").stat().st_size > 30000 * 291 * 8
