@@ -286,7 +286,14 @@ __device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_tra
 				p0.x = ec.x + dist * ed.x;
 				p0.y = ec.y + dist * ed.y;
 				p0.z = ec.z + dist * ed.z;
-				z_id = lk_z_index(c, p0.z);
+				if (c.monotonic && ed.z >= 0.) { /* the march only moves forward: the index follows incrementally */
+					if (!(c.z[z_id] <= p0.z))
+						z_id = lk_z_index(c, p0.z);
+					while (z_id + 1 < nm && c.z[z_id + 1] <= p0.z)
+						z_id++;
+				} else {
+					z_id = lk_z_index(c, p0.z);
+				}
 				ext_here = ((c.ext[z_id + 1] - c.ext[z_id]) / (c.z[z_id + 1] - c.z[z_id])) * (p0.z - c.z[z_id]) + c.ext[z_id];
 				double rad_here = ((c.cap[z_id + 1] - c.cap[z_id]) / (c.z[z_id + 1] - c.z[z_id])) * (p0.z - c.z[z_id]) + c.cap[z_id];
 				hexz = ext_here / (2. * PCB_COSPI_6 * (n_shells + 1));
