@@ -41,9 +41,11 @@ WORKLOADS = {
     "ellip": dict(profile=(2, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5), n_cap=200000, sig_rough=0.0,
                   source=(2000.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.0), energies=np.linspace(1, 40, 400), ids=1_000_000,
                   desc="ellipsoidal polycap (ellip_l9 geometry), 1e6 photon ids/step/GPU, 400-energy grid 1-40 keV, leaks off"),
-    "xos1": dict(profile=(2, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5), n_cap=200000, sig_rough=0.0,
+    # BASELINE configs[3]: the measured XOS profile (the z/cap/ext tables of example/xos1.{prf,axs,ext} as stored in the golden
+    # fixture tests/golden/replay_xos1.npz), xos1.inp source and energy grid
+    "xos1": dict(profile_arrays="xos1", n_cap=200000, sig_rough=0.0,
                  source=(2000.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.0), energies=1.0 + 0.1 * np.arange(291), ids=2_000_000,
-                 desc="XOS-like ellipsoidal profile, 2e6 photon ids/step/GPU, 291-energy grid 1-30 keV (xos1.inp grid)"),
+                 desc="XOS measured profile (xos1.prf/.ext tables), 2e6 photon ids/step/GPU, 291-energy grid 1-30 keV (xos1.inp)"),
 }
 
 # algorithmic FP64 flops of the minimal result-equivalent algorithm
@@ -125,7 +127,13 @@ def reference_setup(w):
         raise RuntimeError("oracle/_ref/libpolycap_ref.so is missing (built by oracle/Makefile where /root/reference exists)")
     ref = H.Ref()
     L = ref.L
-    prof = L.polycap_profile_new(*w["profile"], None)
+    if "profile_arrays" in w:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "replay_%s.npz" % w["profile_arrays"]))
+        z, cap, ext = (np.ascontiguousarray(g[k], dtype=np.float64) for k in ("z", "cap", "ext"))
+        prof = L.polycap_profile_new_from_arrays(int(g["nmax"]), ext.ctypes.data_as(H.c_double_p), cap.ctypes.data_as(H.c_double_p),
+                                                 z.ctypes.data_as(H.c_double_p), None)
+    else:
+        prof = L.polycap_profile_new(*w["profile"], None)
     desc = ref.description(prof, w["sig_rough"], w["n_cap"], list(SIO2.keys()), list(SIO2.values()), 2.23)
     src = ref.source(desc, *w["source"], w["energies"])
     return ref, src
@@ -224,7 +232,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    prof = pc.Profile(*w["profile"])
+    if "profile_arrays" in w:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "replay_%s.npz" % w["profile_arrays"]))
+        prof = pc.Profile.new_from_arrays(g["ext"], g["cap"], g["z"])
+    else:
+        prof = pc.Profile(*w["profile"])
     desc = pc.Description(prof, w["sig_rough"], w["n_cap"], SIO2, 2.23)
     src = pc.Source(desc, *w["source"], w["energies"])
     seed = 20000
