@@ -734,9 +734,25 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			}
 		}
 
-		/* ---------------- hand the photons on ---------------- */
-		if (act && next >= 0)
-			t2_push(S.q[next], &q_tail[next], slot);
+		/* ---------------- hand the photons on: one tail reservation per warp and target queue ---------------- */
+		__threadfence_block(); /* the slots' state is visible before their ids are */
+#pragma unroll
+		for (int qk = 0; qk < TQ_N; qk++) {
+			const unsigned mq = __ballot_sync(0xffffffffu, act && next == qk);
+			if (mq) {
+				unsigned tb0 = 0;
+				const int leader = __ffs(mq) - 1;
+				if (lane == leader)
+					tb0 = atomicAdd(&q_tail[qk], (unsigned)__popc(mq));
+				tb0 = __shfl_sync(0xffffffffu, tb0, leader);
+				if (act && next == qk) {
+					volatile unsigned short *e = &S.q[qk][(tb0 + __popc(mq & ((1u << lane) - 1u))) & (T2_QCAP - 1)];
+					while (*e != T2_EMPTY) {
+					}
+					*e = (unsigned short)slot;
+				}
+			}
+		}
 	}
 #undef T2_SCAN_STEPS
 #undef T2_TRACE_BEGIN
