@@ -104,6 +104,11 @@ POLYCAP_EXTERN int64_t polycap_b200_session_kernels(polycap_b200_session *sessio
 /* FP64 FMA throughput of `device` in TFLOP/s (2 flops per DFMA) -- the roofline denominator */
 POLYCAP_EXTERN double polycap_b200_dfma_peak_tflops(int device, int iters);
 
+/* Device self-test of the shared-divisor division the kernels use in place of repeated `a / b` (pcb_math.h): compares it
+ * with the compiler's IEEE division on `n` pseudo-random operand pairs spanning `span` binades either side of 1
+ * (>= 1100 includes zeros, subnormals, infinities, NaNs).  Returns the number of bit mismatches (0 expected), -1 on error. */
+POLYCAP_EXTERN int64_t polycap_b200_selftest_division(int device, int64_t n, uint64_t seed, int span);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,7 @@ _session_timing = _sig("polycap_b200_session_timing", None, [_v, C.c_int])
 _session_trace_ms = _sig("polycap_b200_session_trace_ms", C.c_double, [_v, c_int64_p])
 _session_kernels = _sig("polycap_b200_session_kernels", C.c_int64, [_v, c_int64_p])
 _dfma_peak = _sig("polycap_b200_dfma_peak_tflops", C.c_double, [C.c_int, C.c_int])
+_selftest_division = _sig("polycap_b200_selftest_division", C.c_int64, [C.c_int, C.c_int64, C.c_uint64, C.c_int])
 
 
 def _raise(err):
@@ -168,6 +169,11 @@ def optconst_provider():
 
 def dfma_peak_tflops(device=-1, iters=200000):
     return _dfma_peak(device, iters)
+
+
+def selftest_division(n=1 << 24, seed=1, span=40, device=-1):
+    """bit mismatches between the kernels' shared-divisor division and IEEE a / b over n operand pairs (0 expected)"""
+    return _selftest_division(device, n, seed, span)
 
 
 _SYMBOLS = ("H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y Zr Nb Mo Tc Ru Rh Pd "

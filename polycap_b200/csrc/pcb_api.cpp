@@ -1432,4 +1432,5 @@ extern "C" int64_t polycap_b200_session_kernels(polycap_b200_session *session, i
 	return session ? pcb_gpu_optic_kernels(session->g, n_trace_kernels) : 0;
 }
 
+extern "C" int64_t polycap_b200_selftest_division(int device, int64_t n, uint64_t seed, int span) { return pcb_gpu_div_selftest(device, n, seed, span); }
 extern "C" double polycap_b200_dfma_peak_tflops(int device, int iters) { return pcb_gpu_dfma_peak(device, iters > 0 ? iters : 200000); }

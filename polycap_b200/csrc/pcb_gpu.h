@@ -104,6 +104,7 @@ int pcb_gpu_sync(int device, void *stream);
 
 /* FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), timed with CUDA events */
 double pcb_gpu_dfma_peak(int device, int iters);
+long long pcb_gpu_div_selftest(int device, long long n, unsigned long long seed, int span);
 
 #ifdef __cplusplus
 }

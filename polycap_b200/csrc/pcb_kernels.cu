@@ -998,6 +998,55 @@ extern "C" int pcb_gpu_sync(int device, void *stream)
 	return 0;
 }
 
+/* ------------------------------------------------------------------ division self-test */
+
+/* pcb_div(a, pcb_divisor(b)) against the compiler's a / b on pseudo-random operand pairs whose exponents cover
+ * `span` binades either side of 1 (span >= 1100 reaches zeros, subnormals, infinities and NaNs); counts bit mismatches */
+__global__ void div_selftest_kernel(unsigned long long n, unsigned long long seed, int span, unsigned long long *bad)
+{
+	unsigned long long local = 0;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+		Philox rng;
+		rng.init(seed, i);
+		double v[2];
+		for (int k = 0; k < 2; k++) {
+			rng.block((uint32_t)k);
+			const unsigned long long m = ((unsigned long long)rng.cache[0] << 32 | rng.cache[1]) & 0x800fffffffffffffULL;
+			const unsigned sel = rng.cache[2];
+			long long e = 1023 + (long long)(sel % (2u * span + 1u)) - span;
+			e = e < 0 ? 0 : (e > 2047 ? 2047 : e);
+			unsigned long long bits = m | ((unsigned long long)e << 52);
+			if ((sel >> 28) == 0)
+				bits &= 0xfff0000000000000ULL; /* powers of two, zeros, infinities */
+			if ((sel >> 28) == 1)
+				bits |= 0x000fffffffffffffULL; /* all-ones significands */
+			v[k] = __longlong_as_double((long long)bits);
+		}
+		const PcbDivisor d = pcb_divisor(v[1]);
+		const double q = pcb_div(v[0], d), r = v[0] / v[1];
+		const bool same = (__double_as_longlong(q) == __double_as_longlong(r)) || (q != q && r != r);
+		if (!same)
+			local++;
+	}
+	if (local)
+		atomicAdd(bad, local);
+}
+
+extern "C" long long pcb_gpu_div_selftest(int device, long long n, unsigned long long seed, int span)
+{
+	device = pick_device(device);
+	if (cudaSetDevice(device) != cudaSuccess)
+		return -1;
+	unsigned long long *d = nullptr, h = 0;
+	if (cudaMalloc(&d, 8) != cudaSuccess)
+		return -1;
+	cudaMemset(d, 0, 8);
+	div_selftest_kernel<<<1184, 256>>>((unsigned long long)n, seed, span, d);
+	const cudaError_t rc = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return rc == cudaSuccess ? (long long)h : -1;
+}
+
 /* ------------------------------------------------------------------ FP64 peak */
 
 __global__ void dfma_peak_kernel(double *out, int iters)

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 		dx = d.x; dy = d.y; dz = d.z;
 		lhx = ex; lhy = ey; lhz = ez;
 		iseg = ix;
-		inv_dz = 1.0 / dz;
+		inv_dz = pcb_rcp_near(dz);
 		if (iseg < nmax) {
 			/* "No wall hit possible in segment iseg" needs the photon inside the bore at both ends (convexity).
 			 * Restarting on the wall the same holds from the hit point on: distance-to-axis minus radius is convex in z,
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 				double z0 = T.z[i], z1 = T.z[i + 1];
 				V3 c0 = {A * T.hexz[i], B * T.hexz[i], z0};
 				V3 c1 = {A * T.hexz[i + 1], B * T.hexz[i + 1], z1};
-				V3 p0 = {ex + dx * (z0 - ez) / dz, ey + dy * (z0 - ez) / dz, z0};
+				const PcbDivisor dz_d = pcb_divisor(dz);
+				V3 p0 = {ex + pcb_div(dx * (z0 - ez), dz_d), ey + pcb_div(dy * (z0 - ez), dz_d), z0};
 				bool bail = false;
 				if (slow) { /* capil.c:1263-1266 */
 					if (within_pc(T.ext[i], c0.x, c0.y) == 0 || within_pc(T.ext[i + 1], c1.x, c1.y) == 0) {
@@ -264,8 +265,7 @@ __global__ void __launch_bounds__(PCB_LB_THREADS, PCB_LB_CTAS) pcb_trace_kernel(
 					}
 					double ca = dot3(sn, pd);
 					if (iesc == 1) { /* capil.c:1270-1273; sn is zero otherwise and acos(0) passes */
-						double ac = acos(ca);
-						if (ac > PCB_PI / 2. || ac < 0.)
+						if (pcb_acos_is_obtuse(ca))
 							iesc = -5;
 						lhx = hit.x; lhy = hit.y; lhz = hit.z; /* photon_coord keeps the last accepted root */
 					}

@@ -49,7 +49,8 @@ struct T2Shared { /* pointers into dynamic shared memory */
 	int *irefl, *ix, *iseg, *ntrace;
 	unsigned char *flags;
 	signed char *code;
-	volatile unsigned short *q[TQ_N];
+	volatile unsigned short *qbase; /* TQ_N rings of T2_QCAP entries, back to back */
+	__device__ __forceinline__ volatile unsigned short *q(int k) const { return qbase + k * T2_QCAP; }
 };
 
 enum { D_EX = 0, D_EY, D_EZ, D_DX, D_DY, D_DZ, D_VX, D_VY, D_VZ, D_LHX, D_LHY, D_LHZ, D_DTRAV, D_A, D_B, D_AUX, D_N };
@@ -95,10 +96,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	S.ix = reinterpret_cast<int *>(p); p += T2_NP * 4;
 	S.iseg = reinterpret_cast<int *>(p); p += T2_NP * 4;
 	S.ntrace = reinterpret_cast<int *>(p); p += T2_NP * 4;
-	for (int k = 0; k < TQ_N; k++) {
-		S.q[k] = reinterpret_cast<volatile unsigned short *>(p);
-		p += T2_QCAP * 2;
-	}
+	S.qbase = reinterpret_cast<volatile unsigned short *>(p);
+	p += TQ_N * T2_QCAP * 2;
 	unsigned short *batch = reinterpret_cast<unsigned short *>(p) + warp * 32; /* slots of this warp's current batch */
 	p += (T2_THREADS / 32) * 32 * 2;
 	S.flags = p; p += T2_NP;
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	for (int i = threadIdx.x; i < TQ_N * T2_QCAP; i += blockDim.x)
-		S.q[i / T2_QCAP][i % T2_QCAP] = T2_EMPTY;
+		S.qbase[i] = T2_EMPTY;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tma_bar)), "r"(3 * tb) : "memory");
@@ -124,7 +123,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		live = T2_NP;
 	}
 	for (int i = threadIdx.x; i < T2_NP; i += blockDim.x)
-		S.q[TQ_NEW][i] = (unsigned short)i;
+		S.q(TQ_NEW)[i] = (unsigned short)i;
 	{
 		uint32_t done = 0;
 		while (!done) {
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				if ((on_wall) && !steep_) {                                                           \
 					in_ = true;                                                                   \
 				} else {                                                                              \
-					const double t_ = (T.z[iseg] - ez) * (1.0 / dz);                              \
+					const double t_ = (T.z[iseg] - ez) * pcb_rcp_near(dz);                        \
 					const double hz_ = T.hexz[iseg];                                              \
 					const double ux_ = pcb_fma(-A, hz_, pcb_fma(dx, t_, ex));                     \
 					const double uy_ = pcb_fma(-B, hz_, pcb_fma(dy, t_, ey));                     \
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	 * Leaves next = TQ_HIT (candidate segment found), TQ_DONE (flew out of the end) or TQ_SCAN (budget used up). */
 #define T2_SCAN_STEPS(K)                                                                                               \
 	do {                                                                                                          \
-		const double inv_dz_ = 1.0 / dz;                                                                      \
+		const double inv_dz_ = pcb_rcp_near(dz);                                                              \
 		bool in_cur_ = flags & F_INCUR;                                                                       \
 		const bool slow_ = flags & F_SLOW;                                                                    \
 		next = TQ_SCAN;                                                                                       \
@@ -223,13 +222,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			const unsigned any = __ballot_sync(0xffffffffu, cnt > 0u);
 			/* a full batch of wall hits first (then long scans, finished photons, free slots); without any full batch, recycle
 			 * slots first (DONE, NEW: cheap, and they put more photons in flight) and take a partial HIT batch last */
-			const int order_full[TQ_N] = {TQ_HIT, TQ_SCAN, TQ_DONE, TQ_NEW};
-			const int order_any[TQ_N] = {TQ_DONE, TQ_NEW, TQ_SCAN, TQ_HIT};
+			const unsigned order_full = TQ_HIT | (TQ_SCAN << 4) | (TQ_DONE << 8) | (TQ_NEW << 12); /* nibble k = k-th choice */
+			const unsigned order_any = TQ_DONE | (TQ_NEW << 4) | (TQ_SCAN << 8) | (TQ_HIT << 12);
 			const unsigned pick = full ? full : any;
 			if (pick) {
 #pragma unroll
 				for (int k = TQ_N - 1; k >= 0; k--) {
-					const int qk = full ? order_full[k] : order_any[k];
+					const int qk = ((full ? order_full : order_any) >> (4 * k)) & 15;
 					if (pick & (1u << qk))
 						type = qk;
 				}
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		const bool act = lane < n;
 		unsigned slot = 0;
 		if (act) {
-			volatile unsigned short *e = &S.q[type][(base + lane) & (T2_QCAP - 1)];
+			volatile unsigned short *e = &S.q(type)[(base + lane) & (T2_QCAP - 1)];
 			unsigned short v;
 			while ((v = *e) == T2_EMPTY) {
 			}
@@ -322,7 +321,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				const double z0 = T.z[i], z1 = T.z[i + 1];
 				V3 c0 = {A * T.hexz[i], B * T.hexz[i], z0};
 				V3 c1 = {A * T.hexz[i + 1], B * T.hexz[i + 1], z1};
-				V3 p0 = {ex + dx * (z0 - ez) / dz, ey + dy * (z0 - ez) / dz, z0};
+				const PcbDivisor dz_d = pcb_divisor(dz);
+				V3 p0 = {ex + pcb_div(dx * (z0 - ez), dz_d), ey + pcb_div(dy * (z0 - ez), dz_d), z0};
 				const double cap0 = __ldg(T.cap + i), cap1 = __ldg(T.cap + i + 1);
 				if (slow && (within_pc(__ldg(T.ext + i), c0.x, c0.y) == 0 || within_pc(__ldg(T.ext + i + 1), c1.x, c1.y) == 0)) { /* capil.c:1263-1266 */
 					code = -1;
@@ -339,8 +339,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					}
 					const double ca = dot3(sn, pd);
 					if (iesc == 1) {
-						const double ac = acos(ca);
-						if (ac > PCB_PI / 2. || ac < 0.)
+						if (pcb_acos_is_obtuse(ca)) /* acos(cosalfa) > M_PI/2, capil.c:1270-1273 */
 							iesc = -5;
 						lhx = hit.x; lhy = hit.y; lhz = hit.z;
 					}
@@ -746,7 +745,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					tb0 = atomicAdd(&q_tail[qk], (unsigned)__popc(mq));
 				tb0 = __shfl_sync(0xffffffffu, tb0, leader);
 				if (act && next == qk) {
-					volatile unsigned short *e = &S.q[qk][(tb0 + __popc(mq & ((1u << lane) - 1u))) & (T2_QCAP - 1)];
+					volatile unsigned short *e = &S.q(qk)[(tb0 + __popc(mq & ((1u << lane) - 1u))) & (T2_QCAP - 1)];
 					while (*e != T2_EMPTY) {
 					}
 					*e = (unsigned short)slot;

@@ -84,3 +84,26 @@ int hm_segment(const double in[20], double out[6])
 	return r;
 }
 }
+// pcb_acos_is_obtuse(x) against the test the reference writes, acos(x) > M_PI/2 (capil.c:1270-1273), with glibc's acos:
+// a dense sweep of the neighbourhood of the edge (in ulps of the edge) plus log-uniform magnitudes of both signs
+extern "C" long hm_obtuse_mismatches(long n)
+{
+	long bad = 0;
+	const double edge = -0x1.cb3b399d747f5p-55;
+	double x = edge;
+	for (int k = 0; k < 4096; k++) x = nextafter(x, -1.0);
+	for (int k = 0; k < 8192; k++, x = nextafter(x, 1.0))
+		if (pcb_acos_is_obtuse(x) != (acos(x) > M_PI / 2. || acos(x) < 0.)) bad++;
+	uint64_t s = 4242;
+	for (long i = 0; i < n; i++) {
+		double m = pow(10., -20. * uni(s));
+		if (i & 1) m = -m;
+		if (pcb_acos_is_obtuse(m) != (acos(m) > M_PI / 2. || acos(m) < 0.)) bad++;
+		double f = edge * (0.5 + uni(s)); /* within a factor 2 of the edge */
+		if (pcb_acos_is_obtuse(f) != (acos(f) > M_PI / 2. || acos(f) < 0.)) bad++;
+	}
+	const double sp[] = {0.0, -0.0, 1.0, -1.0, 1.5, -1.5, NAN, 0x1p-55, -0x1p-55, 0x1p-54, -0x1p-54, -0x1p-53, -0x1p-52};
+	for (double v : sp)
+		if (pcb_acos_is_obtuse(v) != (acos(v) > M_PI / 2. || acos(v) < 0.)) bad++;
+	return bad;
+}

@@ -303,3 +303,10 @@ def test_session_device_tallies(pc):
     assert np.allclose(t_sum.cpu().numpy(), sw, rtol=1e-12)
     c = t_cnt.cpu().numpy()
     assert c[0] == 100000 and c[1] == cnt["exit"] and c[6] == cnt["refl_all"]
+
+
+def test_shared_divisor_division_is_ieee(pc):
+    """pcb_math.h::pcb_div (one reciprocal refinement per divisor, used by norm3 / segment_solve) against the compiler's
+    IEEE `a / b` on the device: ordinary magnitudes, wide exponent ranges, and the full range incl. 0 / subnormal / inf / NaN"""
+    for seed, span in ((1, 3), (2, 40), (3, 400), (4, 1000), (5, 1100)):
+        assert pc.selftest_division(1 << 25, seed, span) == 0, (seed, span)

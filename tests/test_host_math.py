@@ -59,6 +59,14 @@ def test_taper_angle_trig_is_glibc_exact(hm):
         assert list(out) == [0, 0, 0], (lo, hi, list(out))
 
 
+@needs_fma
+def test_obtuse_incidence_predicate_matches_acos(hm):
+    """capil.c:1270-1273 rejects a root when acos(n.d) > M_PI/2; the kernels evaluate that as one comparison"""
+    hm.hm_obtuse_mismatches.restype = C.c_long
+    hm.hm_obtuse_mismatches.argtypes = [C.c_long]
+    assert hm.hm_obtuse_mismatches(300000) == 0
+
+
 def test_complex_helpers_match_c99(hm):
     """csqrt / cabs / 1/z as libgcc + glibc evaluate them for the Fresnel term (capil.c:497-511)"""
     out = (C.c_long * 3)()
