@@ -32,6 +32,9 @@
 #define T2_NP 1152 /* photon slots per CTA */
 #endif
 #define T2_QCAP 2048 /* ring capacity, power of two > T2_NP */
+#ifndef T2_LANE_NE
+#define T2_LANE_NE 32 /* up to this many energies a lane walks its own photon's weight vector; above, pairs are dealt over the warp */
+#endif
 #define T2_EMPTY 0xFFFFu
 
 enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_DONE, TQ_N };
@@ -39,7 +42,7 @@ enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_DONE, TQ_N };
 /* flag bits of a photon slot */
 enum { F_SLOW = 1, F_DEEP = 2, F_WINIT = 4, F_INCUR = 8, F_INNXT = 16 };
 
-struct T2Dbl { /* the 16 double fields of the pool: ex ey ez dx dy dz vx vy vz lhx lhy lhz dtrav A B aux, each [T2_NP] */
+struct T2Dbl { /* the 16 double fields of the pool: ex ey ez dx dy dz vx vy vz g0 g1 lhz dtrav A B aux (g0, g1, lhz, aux double as the staging of the reflection geometry), each [T2_NP] */
 	double *base;
 	__device__ __forceinline__ double *operator[](int k) const { return base + k * T2_NP; }
 };
@@ -102,6 +105,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	p += (T2_THREADS / 32) * 32 * 2;
 	S.flags = p; p += T2_NP;
 	S.code = reinterpret_cast<signed char *>(p); p += T2_NP;
+	p += (16 - (2 * T2_NP) % 16) % 16;
+	unsigned *wstat = reinterpret_cast<unsigned *>(p);
+	p += (T2_THREADS / 32) * 16 * 4;
+	double *ecs = reinterpret_cast<double *>(p); /* optical constants n, 1/n^2, k*r rows (EC_NRE .. EC_KR) when nE <= T2_LANE_NE */
+	p += 5 * T2_LANE_NE * 8;
+	const bool lane_ne = nE <= T2_LANE_NE;
 
 	if (threadIdx.x == 0) {
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tma_bar)));
@@ -124,6 +133,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	}
 	for (int i = threadIdx.x; i < T2_NP; i += blockDim.x)
 		S.q(TQ_NEW)[i] = (unsigned short)i;
+	if (lane_ne)
+		for (int i = threadIdx.x; i < 5 * nE; i += blockDim.x)
+			ecs[i] = o.ec[i];
+	if (threadIdx.x < (T2_THREADS / 32) * 16)
+		wstat[threadIdx.x] = 0;
 	{
 		uint32_t done = 0;
 		while (!done) {
@@ -137,8 +151,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 
 	const double *ec = o.ec;
 	double *wcta = P.wscratch + (unsigned long long)blockIdx.x * T2_NP * (unsigned long long)nE; /* weight vector of slot s at wcta + s*nE */
-	unsigned int c_steps = 0, c_solves = 0, c_refl = 0, c_launch = 0;
-	unsigned int s_batches = 0, s_lanes = 0, s_empty = 0, s_lost = 0, s_hit_b = 0, s_hit_l = 0, s_scan_b = 0, s_scan_l = 0;
+	/* work and scheduler counters live in shared memory, one row per warp, updated by lane 0 (they would cost 12 registers) */
+	enum { W_STEPS = 0, W_SOLVES, W_REFL, W_LAUNCH, W_BATCHES, W_LANES, W_EMPTY, W_LOST, W_HIT_B, W_HIT_L, W_SCAN_B, W_SCAN_L, W_N = 16 };
+	volatile unsigned *wst = wstat + warp * W_N;
 	volatile unsigned *vhead = q_head, *vtail = q_tail;
 	volatile int *vlive = &live;
 
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			V3 d_ = {dx, dy, dz};                                                                         \
 			norm3(d_);                                                                                    \
 			dx = d_.x; dy = d_.y; dz = d_.z;                                                              \
-			lhx = ex; lhy = ey; lhz = ez;                                                                 \
+			lhz = ez;                                                                                     \
 			iseg = ix;                                                                                    \
 			flags &= ~F_INCUR;                                                                            \
 			if (iseg < nmax) {                                                                            \
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			const bool in_next_ = pcb_fma(ux_, ux_, uy_ * uy_) < T.rm[iseg + 1];                          \
 			if (in_cur_ && in_next_ && !slow_) {                                                          \
 				iseg++;                                                                               \
-				c_steps++;                                                                            \
+				t_steps++;                                                                            \
 				in_cur_ = in_next_;                                                                   \
 			} else {                                                                                      \
 				flags = (flags & ~F_INNXT) | (in_next_ ? F_INNXT : 0);                                \
@@ -246,13 +261,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				n = __shfl_sync(0xffffffffu, n, 0);
 				base = __shfl_sync(0xffffffffu, base, 0);
 				if (n == 0) {
-					s_lost++;
+					if (lane == 0)
+						wst[W_LOST]++;
 					continue; /* lost the race */
 				}
 			} else {
 				if (*vlive == 0)
 					break; /* nothing queued, nothing in flight */
-				s_empty++;
+				if (lane == 0)
+					wst[W_EMPTY]++;
 				__nanosleep(backoff); /* all photons are in other warps' hands: back off so the pollers leave the issue slots alone */
 				if (backoff < 4096u)
 					backoff <<= 1;
@@ -260,10 +277,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			}
 		}
 		backoff = 256u;
-		s_batches++;
-		s_lanes += n;
-		if (type == TQ_HIT) { s_hit_b++; s_hit_l += n; }
-		if (type == TQ_SCAN) { s_scan_b++; s_scan_l += n; }
+		if (lane == 0) {
+			wst[W_BATCHES]++;
+			wst[W_LANES] += n;
+			if (type == TQ_HIT) { wst[W_HIT_B]++; wst[W_HIT_L] += n; wst[W_SOLVES] += n; }
+			if (type == TQ_SCAN) { wst[W_SCAN_B]++; wst[W_SCAN_L] += n; }
+		}
+		unsigned t_steps = 0; /* this lane's segment steps, reflections (<< 16) and launches (<< 24) in this task */
 		const bool act = lane < n;
 		unsigned slot = 0;
 		if (act) {
@@ -276,31 +296,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		}
 		__threadfence_block();
 
-		/* ---------------- photon state: shared memory -> registers ---------------- */
-		double ex = 0, ey = 0, ez = 0, dx = 0, dy = 0, dz = 1, vx = 0, vy = 0, vz = 0, lhx = 0, lhy = 0, lhz = 0, snx = 0, sny = 0, snz = 0;
-		double cosalfa = 0, dtrav = 0, A = 0, B = 0;
-		unsigned lid = 0;
-		int irefl = 0, ix = 0, iseg = 0, ntrace = 0, code = 0;
-		unsigned flags = 0;
-		if (act && type != TQ_NEW) {
-			ex = S.d[D_EX][slot]; ey = S.d[D_EY][slot]; ez = S.d[D_EZ][slot];
-			dx = S.d[D_DX][slot]; dy = S.d[D_DY][slot]; dz = S.d[D_DZ][slot];
-			A = S.d[D_A][slot]; B = S.d[D_B][slot];
-			iseg = S.iseg[slot];
-			flags = S.flags[slot];
-			if (type != TQ_SCAN) {
-				lhx = S.d[D_LHX][slot]; lhy = S.d[D_LHY][slot]; lhz = S.d[D_LHZ][slot];
-				vx = S.d[D_VX][slot]; vy = S.d[D_VY][slot]; vz = S.d[D_VZ][slot];
-				dtrav = S.d[D_DTRAV][slot];
-				ix = S.ix[slot];
-				lid = S.lid[slot]; irefl = S.irefl[slot]; ntrace = S.ntrace[slot]; code = S.code[slot];
-			}
-		}
+		/* Photon fields are read from the slot when a phase needs them and written back as soon as they are final, so that
+		 * few of them are live at any point (96 registers per thread, 640 threads). */
+#define SD(k) S.d[k][slot]
 		int next = -1; /* queue the photon goes to; -1: slot retired */
 
 		if (type == TQ_SCAN) {
 			/* ---------------- SCAN: continuation of a long free flight ---------------- */
 			if (act) {
+				const double ex = SD(D_EX), ey = SD(D_EY), ez = SD(D_EZ), dx = SD(D_DX), dy = SD(D_DY), dz = SD(D_DZ), A = SD(D_A), B = SD(D_B);
+				int iseg = S.iseg[slot], code = 0;
+				unsigned flags = S.flags[slot];
 				T2_SCAN_STEPS(64);
 				S.iseg[slot] = iseg;
 				S.flags[slot] = (unsigned char)flags;
@@ -309,15 +315,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			}
 		} else if (type == TQ_HIT) {
 			/* ---------------- HIT: solve the candidate segment (capil.c:1256-1309); on a hit the reflection: travel and in-optic
-			 * checks (capil.c:1315-1343), capil_reflect preamble + geometry, the energy loop over the batch's (photon, energy)
-			 * pairs, the specular direction and the start of the next capil_trace call; then scan on to the next candidate ---------------- */
+			 * checks (capil.c:1315-1343), capil_reflect preamble + geometry, the energy loop, the specular direction and the
+			 * start of the next capil_trace call; then scan on to the next candidate ---------------- */
 			bool hitting = false;
-			double alfa = 0;
+			double dx = 0, dy = 0, dz = 1, snx = 0, sny = 0, snz = 0, cosalfa = 0; /* live through the energy loop */
+			double g_ct = 0, g_st = 0, g_fs = 0, alfa = 0;
+			unsigned flags = 0;
+			int iseg = 0, ix = 0, code = 0;
 			if (act) {
+				flags = S.flags[slot];
+				iseg = S.iseg[slot];
+				double ex = SD(D_EX), ey = SD(D_EY), ez = SD(D_EZ);
+				dx = SD(D_DX); dy = SD(D_DY); dz = SD(D_DZ);
+				const double A = SD(D_A), B = SD(D_B);
 				const bool slow = flags & F_SLOW;
 				const int i = iseg;
-				c_steps++;
-				c_solves++;
+				t_steps++;
 				const double z0 = T.z[i], z1 = T.z[i + 1];
 				V3 c0 = {A * T.hexz[i], B * T.hexz[i], z0};
 				V3 c1 = {A * T.hexz[i + 1], B * T.hexz[i + 1], z1};
@@ -328,20 +341,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					code = -1;
 					next = TQ_DONE;
 				} else {
-					V3 hit = {lhx, lhy, lhz}, sn;
+					V3 hit = {0., 0., 0.}, sn;
 					V3 pd = {dx, dy, dz};
 					int iesc;
 					if (z0 < 0. || z1 < 0 || cap0 < 0. || cap1 < 0. || dz < 0 || z1 <= z0) {
 						iesc = -1;
 						sn.x = sn.y = sn.z = 0.0;
 					} else {
-						iesc = segment_solve(c0, c1, cap0, cap1, p0, pd, lhz, hit, sn);
+						iesc = segment_solve(c0, c1, cap0, cap1, p0, pd, SD(D_LHZ), hit, sn);
 					}
 					const double ca = dot3(sn, pd);
 					if (iesc == 1) {
 						if (pcb_acos_is_obtuse(ca)) /* acos(cosalfa) > M_PI/2, capil.c:1270-1273 */
 							iesc = -5;
-						lhx = hit.x; lhy = hit.y; lhz = hit.z;
+						SD(D_LHZ) = hit.z; /* photon_coord keeps the last root, accepted or not; only its z is read again */
 					}
 					if (iesc == 1) {
 						bool outside = false;
@@ -358,6 +371,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 							snx = sn.x; sny = sn.y; snz = sn.z;
 							cosalfa = ca;
 							hitting = true;
+							t_steps += 1u << 16;
+							const double rx = hit.x - ex, ry = hit.y - ey, rz = hit.z - ez;
+							SD(D_DTRAV) = SD(D_DTRAV) + sqrt(rx * rx + ry * ry + rz * rz); /* capil.c:1315-1319 */
+							ex = hit.x; ey = hit.y; ez = hit.z;
+							SD(D_EX) = ex; SD(D_EY) = ey; SD(D_EZ) = ez;
+							if (fabs(cosalfa) > 1.0) {
+								code = -1;
+								next = TQ_DONE;
+								hitting = false;
+							}
 						}
 					} else {
 						bool outside = false;
@@ -366,22 +389,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						if (outside) {
 							code = -1;
 							next = TQ_DONE;
-						} else {
+						} else { /* no wall hit in this segment: on to the next candidate while the photon is in registers */
 							iseg = i + 1;
 							flags = (flags & ~F_INCUR) | ((flags & F_INNXT) ? F_INCUR : 0);
-							next = TQ_SCAN;
+							T2_SCAN_STEPS(24);
 						}
-					}
-				}
-				if (hitting) {
-					c_refl++;
-					const double rx = lhx - ex, ry = lhy - ey, rz = lhz - ez;
-					dtrav += sqrt(rx * rx + ry * ry + rz * rz); /* capil.c:1315-1319 */
-					ex = lhx; ey = lhy; ez = lhz;
-					if (fabs(cosalfa) > 1.0) {
-						code = -1;
-						next = TQ_DONE;
-						hitting = false;
 					}
 				}
 				if (hitting) { /* *ix = last i < nmax with z[i] <= hit z (capil.c:1330-1333) */
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						ix = found;
 					if (slow) { /* capil.c:1334-1343 */
 						const double e0 = __ldg(T.ext + ix), e1 = __ldg(T.ext + ix + 1);
-						const double ext_here = ((e1 - e0) / (T.z[ix + 1] - T.z[ix])) * (lhz - T.z[ix]) + e0;
+						const double ext_here = ((e1 - e0) / (T.z[ix + 1] - T.z[ix])) * (ez - T.z[ix]) + e0;
 						const bool outside = o.mono ? (ex * ex + ey * ey >= ext_here) : (within_pc(ext_here, ex, ey) == 0);
 						if (outside) {
 							code = -1;
@@ -420,144 +432,193 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						next = TQ_DONE;
 						hitting = false;
 					} else {
-						V3 ev = {vx, vy, vz};
+						V3 ev = {SD(D_VX), SD(D_VY), SD(D_VZ)};
 						ReflGeom g;
 						if (EXACT_W)
 							refl_geometry(sn, d, ev, g);
 						else
 							refl_geometry_fast(sn, d, ev, g);
-						vx = g.new_ev.x; vy = g.new_ev.y; vz = g.new_ev.z;
-						/* geometry for the pair loop, readable by every lane: the slot's photon_coord fields (free until the
-						 * next trace call) and aux */
-						S.d[D_LHX][slot] = g.cos_t; S.d[D_LHY][slot] = g.sin_t; S.d[D_LHZ][slot] = g.frac_s;
-						S.d[D_AUX][slot] = alfa;
+						SD(D_VX) = g.new_ev.x; SD(D_VY) = g.new_ev.y; SD(D_VZ) = g.new_ev.z;
+						g_ct = g.cos_t; g_st = g.sin_t; g_fs = g.frac_s;
 					}
 				}
 			}
-			/* ---- energy loop (capil.c:625-645) over the reflecting photons of the batch ---- */
-			const unsigned go = __ballot_sync(0xffffffffu, hitting);
-			const int n_go = __popc(go);
-			if (hitting) {
-				batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
-				if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
-					double *w0 = wcta + (unsigned long long)slot * nE;
-					for (int e2 = 0; e2 < nE; e2++)
-						w0[e2] = 1.0;
-				}
-			}
-			__syncwarp();
-			const int total = n_go * nE;
+			/* ---- energy loop (capil.c:625-645) ---- */
 			const bool rough = (o.sig_rough != 0.0);
 			const double sig_rough = o.sig_rough;
-			unsigned alive_bits = 0, bad_bits = 0; /* bit k: k-th reflecting photon of the batch */
-			int pi = lane / nE, e = lane - pi * nE;
-			const int dpi = 32 / nE, de = 32 - dpi * nE;
-			int j0 = 0;
-			if (!EXACT_W) {
-				enum { U = 2 };
-				int pu[U], eu[U];
-				pu[0] = pi; eu[0] = e;
-#pragma unroll
-				for (int u = 1; u < U; u++) {
-					pu[u] = pu[u - 1] + dpi; eu[u] = eu[u - 1] + de;
-					if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
-				}
-				const int dpiU = (32 * U) / nE, deU = 32 * U - dpiU * nE;
-				for (; j0 + 32 * U <= total; j0 += 32 * U) {
-					unsigned sl[U];
-					double *wp[U];
-					double w[U], r[U];
-#pragma unroll
-					for (int u = 0; u < U; u++) {
-						sl[u] = batch[pu[u]];
-						wp[u] = wcta + (unsigned long long)sl[u] * nE + eu[u];
-						w[u] = *wp[u];
-					}
-#pragma unroll
-					for (int u = 0; u < U; u++)
-						r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
-									 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_LHX][sl[u]], S.d[D_LHY][sl[u]], S.d[D_LHZ][sl[u]],
-									 1. - S.d[D_LHZ][sl[u]]);
-#pragma unroll
-					for (int u = 0; u < U; u++) {
+			bool w_alive = false, w_bad = false;
+			if (lane_ne) {
+				/* few energies: every reflecting lane walks its own photon's weight vector, two energies in flight;
+				 * the optical constants come from shared memory (one broadcast read per warp) */
+				if (hitting) {
+					double *w = wcta + (unsigned long long)slot * nE;
+					const bool first = !(flags & F_WINIT); /* first reflection: the weight vector starts at 1 */
+					const double g_fp = 1. - g_fs;
+					int e = 0;
+					for (; e + 2 <= nE; e += 2) {
+						double w0 = first ? 1.0 : w[e], w1 = first ? 1.0 : w[e + 1];
+						const double r0 = EXACT_W ? fresnel_rtot(ecs[EC_NRE * nE + e], ecs[EC_NIM * nE + e], ecs[EC_I2RE * nE + e], ecs[EC_I2IM * nE + e], g_ct, g_st, g_fs, g_fp)
+									  : fresnel_rtot_fast(ecs[EC_NRE * nE + e], ecs[EC_NIM * nE + e], ecs[EC_I2RE * nE + e], ecs[EC_I2IM * nE + e], g_ct, g_st, g_fs, g_fp);
+						const double r1 = EXACT_W ? fresnel_rtot(ecs[EC_NRE * nE + e + 1], ecs[EC_NIM * nE + e + 1], ecs[EC_I2RE * nE + e + 1], ecs[EC_I2IM * nE + e + 1], g_ct, g_st, g_fs, g_fp)
+									  : fresnel_rtot_fast(ecs[EC_NRE * nE + e + 1], ecs[EC_NIM * nE + e + 1], ecs[EC_I2RE * nE + e + 1], ecs[EC_I2IM * nE + e + 1], g_ct, g_st, g_fs, g_fp);
 						if (rough) {
-							const double cr = __ldg(ec + EC_KR * nE + eu[u]) * S.d[D_AUX][sl[u]] * sig_rough;
-							w[u] = w[u] * r[u] * exp(-1. * cr * cr);
+							const double c0r = ecs[EC_KR * nE + e] * alfa * sig_rough, c1r = ecs[EC_KR * nE + e + 1] * alfa * sig_rough;
+							w0 = w0 * r0 * exp(-1. * c0r * c0r);
+							w1 = w1 * r1 * exp(-1. * c1r * c1r);
 						} else {
-							w[u] = w[u] * r[u] * 1.0;
+							w0 = w0 * r0 * 1.0;
+							w1 = w1 * r1 * 1.0;
 						}
-						*wp[u] = w[u];
-						if (r[u] < 0. || r[u] > 1.)
-							bad_bits |= 1u << pu[u];
-						if (w[u] >= 1.e-4)
-							alive_bits |= 1u << pu[u];
-						pu[u] += dpiU; eu[u] += deU;
+						w[e] = w0;
+						w[e + 1] = w1;
+						w_bad |= (r0 < 0. || r0 > 1.) || (r1 < 0. || r1 > 1.);
+						w_alive |= (w0 >= 1.e-4) || (w1 >= 1.e-4);
+					}
+					if (e < nE) {
+						double w0 = first ? 1.0 : w[e];
+						const double r0 = EXACT_W ? fresnel_rtot(ecs[EC_NRE * nE + e], ecs[EC_NIM * nE + e], ecs[EC_I2RE * nE + e], ecs[EC_I2IM * nE + e], g_ct, g_st, g_fs, g_fp)
+									  : fresnel_rtot_fast(ecs[EC_NRE * nE + e], ecs[EC_NIM * nE + e], ecs[EC_I2RE * nE + e], ecs[EC_I2IM * nE + e], g_ct, g_st, g_fs, g_fp);
+						if (rough) {
+							const double c0r = ecs[EC_KR * nE + e] * alfa * sig_rough;
+							w0 = w0 * r0 * exp(-1. * c0r * c0r);
+						} else {
+							w0 = w0 * r0 * 1.0;
+						}
+						w[e] = w0;
+						w_bad |= (r0 < 0. || r0 > 1.);
+						w_alive |= (w0 >= 1.e-4);
+					}
+				}
+			} else {
+				/* many energies: the batch's (photon, energy) pairs are dealt over all lanes.  The geometry of each reflecting photon
+				 * is staged in its slot (fields that are rewritten before they are read again), readable by every lane */
+				const unsigned go = __ballot_sync(0xffffffffu, hitting);
+				const int n_go = __popc(go);
+				if (hitting) {
+					SD(D_LHX) = g_ct; SD(D_LHY) = g_st; SD(D_LHZ) = g_fs; SD(D_AUX) = alfa;
+					batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
+					if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
+						double *w0 = wcta + (unsigned long long)slot * nE;
+						for (int e2 = 0; e2 < nE; e2++)
+							w0[e2] = 1.0;
+					}
+				}
+				__syncwarp();
+				const int total = n_go * nE;
+				unsigned alive_bits = 0, bad_bits = 0; /* bit k: k-th reflecting photon of the batch */
+				int pi = lane / nE, e = lane - pi * nE;
+				const int dpi = 32 / nE, de = 32 - dpi * nE;
+				int j0 = 0;
+				if (!EXACT_W) {
+					enum { U = 2 };
+					int pu[U], eu[U];
+					pu[0] = pi; eu[0] = e;
+#pragma unroll
+					for (int u = 1; u < U; u++) {
+						pu[u] = pu[u - 1] + dpi; eu[u] = eu[u - 1] + de;
 						if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
 					}
-				}
-				pi = pu[0];
-				e = eu[0];
-			}
-			for (; j0 < total; j0 += 32) {
-				if (j0 + lane < total) {
-					const unsigned sl = batch[pi];
-					double *wp = wcta + (unsigned long long)sl * nE + e;
-					double w = *wp;
-					const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
-					const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
-					const double c_t = S.d[D_LHX][sl], s_t = S.d[D_LHY][sl], f_s = S.d[D_LHZ][sl];
-					const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s)
-								    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s);
-					if (rough) {
-						const double cons1 = __ldg(ec + EC_KR * nE + e) * S.d[D_AUX][sl] * sig_rough;
-						w = w * rtot * exp(-1. * cons1 * cons1);
-					} else {
-						w = w * rtot * 1.0;
+					const int dpiU = (32 * U) / nE, deU = 32 * U - dpiU * nE;
+					for (; j0 + 32 * U <= total; j0 += 32 * U) {
+						unsigned sl[U];
+						double *wp[U];
+						double w[U], r[U];
+#pragma unroll
+						for (int u = 0; u < U; u++) {
+							sl[u] = batch[pu[u]];
+							wp[u] = wcta + (unsigned long long)sl[u] * nE + eu[u];
+							w[u] = *wp[u];
+						}
+#pragma unroll
+						for (int u = 0; u < U; u++)
+							r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
+										 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_LHX][sl[u]], S.d[D_LHY][sl[u]], S.d[D_LHZ][sl[u]],
+										 1. - S.d[D_LHZ][sl[u]]);
+#pragma unroll
+						for (int u = 0; u < U; u++) {
+							if (rough) {
+								const double cr = __ldg(ec + EC_KR * nE + eu[u]) * S.d[D_AUX][sl[u]] * sig_rough;
+								w[u] = w[u] * r[u] * exp(-1. * cr * cr);
+							} else {
+								w[u] = w[u] * r[u] * 1.0;
+							}
+							*wp[u] = w[u];
+							if (r[u] < 0. || r[u] > 1.)
+								bad_bits |= 1u << pu[u];
+							if (w[u] >= 1.e-4)
+								alive_bits |= 1u << pu[u];
+							pu[u] += dpiU; eu[u] += deU;
+							if (eu[u] >= nE) { eu[u] -= nE; pu[u]++; }
+						}
 					}
-					*wp = w;
-					if (rtot < 0. || rtot > 1.)
-						bad_bits |= 1u << pi;
-					if (w >= 1.e-4)
-						alive_bits |= 1u << pi;
+					pi = pu[0];
+					e = eu[0];
 				}
-				pi += dpi;
-				e += de;
-				if (e >= nE) {
-					e -= nE;
-					pi++;
+				for (; j0 < total; j0 += 32) {
+					if (j0 + lane < total) {
+						const unsigned sl = batch[pi];
+						double *wp = wcta + (unsigned long long)sl * nE + e;
+						double w = *wp;
+						const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
+						const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
+						const double c_t = S.d[D_LHX][sl], s_t = S.d[D_LHY][sl], f_s = S.d[D_LHZ][sl];
+						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s)
+									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s);
+						if (rough) {
+							const double cons1 = __ldg(ec + EC_KR * nE + e) * S.d[D_AUX][sl] * sig_rough;
+							w = w * rtot * exp(-1. * cons1 * cons1);
+						} else {
+							w = w * rtot * 1.0;
+						}
+						*wp = w;
+						if (rtot < 0. || rtot > 1.)
+							bad_bits |= 1u << pi;
+						if (w >= 1.e-4)
+							alive_bits |= 1u << pi;
+					}
+					pi += dpi;
+					e += de;
+					if (e >= nE) {
+						e -= nE;
+						pi++;
+					}
 				}
-			}
-			alive_bits = __reduce_or_sync(0xffffffffu, alive_bits);
-			bad_bits = __reduce_or_sync(0xffffffffu, bad_bits);
-			if (hitting) {
+				alive_bits = __reduce_or_sync(0xffffffffu, alive_bits);
+				bad_bits = __reduce_or_sync(0xffffffffu, bad_bits);
 				const int rank = __popc(go & ((1u << lane) - 1u));
+				w_alive = (alive_bits >> rank) & 1u;
+				w_bad = (bad_bits >> rank) & 1u;
+			}
+			if (hitting) {
 				flags |= F_WINIT;
-				if ((bad_bits >> rank) & 1u) {
+				if (w_bad) {
 					code = -1;
 					next = TQ_DONE;
-				} else if ((alive_bits >> rank) & 1u) { /* capil.c:1346-1352 */
+				} else if (w_alive) { /* capil.c:1346-1352 */
 					dx = dx - 2.0 * cosalfa * snx;
 					dy = dy - 2.0 * cosalfa * sny;
 					dz = dz - 2.0 * cosalfa * snz;
 					V3 d = {dx, dy, dz};
 					norm3(d);
 					dx = d.x; dy = d.y; dz = d.z;
-					irefl++;
+					S.irefl[slot] = S.irefl[slot] + 1;
+					const double ex = SD(D_EX), ey = SD(D_EY), ez = SD(D_EZ), A = SD(D_A), B = SD(D_B);
+					int ntrace = S.ntrace[slot];
+					double lhz;
 					T2_TRACE_BEGIN(true);
+					if (next == TQ_SCAN) {
+						S.ntrace[slot] = ntrace;
+						SD(D_LHZ) = lhz;
+						T2_SCAN_STEPS(24);
+					}
 				} else {
 					code = 0;
 					next = TQ_DONE;
 				}
 			}
 			if (act) {
-				if (next == TQ_SCAN) /* on to the next candidate segment while the photon is in registers */
-					T2_SCAN_STEPS(24);
-				S.d[D_EX][slot] = ex; S.d[D_EY][slot] = ey; S.d[D_EZ][slot] = ez;
-				S.d[D_DX][slot] = dx; S.d[D_DY][slot] = dy; S.d[D_DZ][slot] = dz;
-				S.d[D_VX][slot] = vx; S.d[D_VY][slot] = vy; S.d[D_VZ][slot] = vz;
-				S.d[D_LHX][slot] = lhx; S.d[D_LHY][slot] = lhy; S.d[D_LHZ][slot] = lhz;
-				S.d[D_DTRAV][slot] = dtrav;
-				S.iseg[slot] = iseg; S.ix[slot] = ix; S.irefl[slot] = irefl; S.ntrace[slot] = ntrace;
+				SD(D_DX) = dx; SD(D_DY) = dy; SD(D_DZ) = dz;
+				S.iseg[slot] = iseg; S.ix[slot] = ix;
 				S.flags[slot] = (unsigned char)flags;
 				S.code[slot] = (signed char)code;
 			}
@@ -565,6 +626,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		} else if (type == TQ_DONE) {
 			/* ---------------- DONE: classify (source.c:758-777), dense per-id outputs ---------------- */
 			if (act) {
+				const double ex = SD(D_EX), ey = SD(D_EY), ez = SD(D_EZ), dx = SD(D_DX), dy = SD(D_DY), dz = SD(D_DZ);
+				const double vx = SD(D_VX), vy = SD(D_VY), vz = SD(D_VZ), dtrav = SD(D_DTRAV);
+				const unsigned lid = S.lid[slot], flags = S.flags[slot];
+				const int irefl = S.irefl[slot], ntrace = S.ntrace[slot], code = S.code[slot];
 				const unsigned long long nn = P.n_ids;
 				const double *wsl = wcta + (unsigned long long)slot * nE;
 				const bool w_init = flags & F_WINIT;
@@ -641,8 +706,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					atomicSub(&live, 1); /* no ids left: the slot retires */
 					next = -1;
 				} else {
-					lid = (unsigned)id;
-					c_launch++;
+					double ex, ey, ez, dx, dy, dz, lhz = 0, A = 0, B = 0;
+					int ix = 0, iseg = 0, ntrace = 0, code = 0;
+					unsigned flags = 0;
+					t_steps += 1u << 24;
 					StartState s0;
 					if (MODE == MODE_SOURCE) {
 						source_sample(P.s, o.mono, P.id0 + id, s0);
@@ -651,13 +718,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						s0.dir.x = P.rin.dir[3 * id]; s0.dir.y = P.rin.dir[3 * id + 1]; s0.dir.z = P.rin.dir[3 * id + 2];
 						s0.ev.x = P.rin.ev[3 * id]; s0.ev.y = P.rin.ev[3 * id + 1]; s0.ev.z = P.rin.ev[3 * id + 2];
 					}
-					irefl = 0; ntrace = 0; dtrav = 0; code = 0; flags = 0;
 					norm3(s0.dir);
 					ex = s0.coords.x; ey = s0.coords.y; ez = s0.coords.z;
 					V3 d = s0.dir;
 					norm3(d);
 					dx = d.x; dy = d.y; dz = d.z;
-					vx = s0.ev.x; vy = s0.ev.y; vz = s0.ev.z;
+					SD(D_VX) = s0.ev.x; SD(D_VY) = s0.ev.y; SD(D_VZ) = s0.ev.z;
 					int z_id = 0;
 					if (ez > 0) {
 						for (int i = 0; i < nmax; i++)
@@ -721,15 +787,24 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 								T2_SCAN_STEPS(24);
 						}
 					}
-					S.d[D_EX][slot] = ex; S.d[D_EY][slot] = ey; S.d[D_EZ][slot] = ez;
-					S.d[D_DX][slot] = dx; S.d[D_DY][slot] = dy; S.d[D_DZ][slot] = dz;
-					S.d[D_VX][slot] = vx; S.d[D_VY][slot] = vy; S.d[D_VZ][slot] = vz;
-					S.d[D_LHX][slot] = lhx; S.d[D_LHY][slot] = lhy; S.d[D_LHZ][slot] = lhz;
-					S.d[D_DTRAV][slot] = dtrav; S.d[D_A][slot] = A; S.d[D_B][slot] = B;
-					S.lid[slot] = lid; S.irefl[slot] = irefl; S.ix[slot] = ix; S.iseg[slot] = iseg; S.ntrace[slot] = ntrace;
+					SD(D_EX) = ex; SD(D_EY) = ey; SD(D_EZ) = ez;
+					SD(D_DX) = dx; SD(D_DY) = dy; SD(D_DZ) = dz;
+					SD(D_LHZ) = lhz;
+					SD(D_DTRAV) = 0.0; SD(D_A) = A; SD(D_B) = B;
+					S.lid[slot] = (unsigned)id; S.irefl[slot] = 0; S.ix[slot] = ix; S.iseg[slot] = iseg; S.ntrace[slot] = ntrace;
 					S.flags[slot] = (unsigned char)flags;
 					S.code[slot] = (signed char)code;
 				}
+			}
+		}
+#undef SD
+
+		{
+			const unsigned tsum = __reduce_add_sync(0xffffffffu, t_steps);
+			if (lane == 0 && tsum) {
+				wst[W_STEPS] += tsum & 0xffffu;
+				wst[W_REFL] += (tsum >> 16) & 0xffu;
+				wst[W_LAUNCH] += tsum >> 24;
 			}
 		}
 
@@ -756,25 +831,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 #undef T2_SCAN_STEPS
 #undef T2_TRACE_BEGIN
 
-	for (int off = 16; off > 0; off >>= 1) {
-		c_steps += __shfl_down_sync(0xffffffffu, c_steps, off);
-		c_solves += __shfl_down_sync(0xffffffffu, c_solves, off);
-		c_refl += __shfl_down_sync(0xffffffffu, c_refl, off);
-		c_launch += __shfl_down_sync(0xffffffffu, c_launch, off);
-	}
 	if (lane == 0) {
-		atomicAdd(&P.wc->seg_steps, (unsigned long long)c_steps);
-		atomicAdd(&P.wc->solves, (unsigned long long)c_solves);
-		atomicAdd(&P.wc->reflections, (unsigned long long)c_refl);
-		atomicAdd(&P.wc->launched, (unsigned long long)c_launch);
-		atomicAdd(&P.wc->dbg[0], (unsigned long long)s_batches);
-		atomicAdd(&P.wc->dbg[1], (unsigned long long)s_lanes);
-		atomicAdd(&P.wc->dbg[2], (unsigned long long)s_empty);
-		atomicAdd(&P.wc->dbg[3], (unsigned long long)s_lost);
-		atomicAdd(&P.wc->dbg[4], (unsigned long long)s_hit_b);
-		atomicAdd(&P.wc->dbg[5], (unsigned long long)s_hit_l);
-		atomicAdd(&P.wc->dbg[6], (unsigned long long)s_scan_b);
-		atomicAdd(&P.wc->dbg[7], (unsigned long long)s_scan_l);
+		atomicAdd(&P.wc->seg_steps, (unsigned long long)wst[W_STEPS]);
+		atomicAdd(&P.wc->solves, (unsigned long long)wst[W_SOLVES]);
+		atomicAdd(&P.wc->reflections, (unsigned long long)wst[W_REFL]);
+		atomicAdd(&P.wc->launched, (unsigned long long)wst[W_LAUNCH]);
+		for (int k = 0; k < 8; k++)
+			atomicAdd(&P.wc->dbg[k], (unsigned long long)wst[W_BATCHES + k]);
 	}
 }
 
@@ -782,7 +845,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 static inline size_t t2_smem_bytes(int tstride)
 {
 	return 3 * (size_t)tstride * 8 + 16 * (size_t)T2_NP * 8 + (size_t)(T2_THREADS / 32) * 32 * 2 + 5 * (size_t)T2_NP * 4 + (size_t)TQ_N * T2_QCAP * 2 +
-	       2 * (size_t)T2_NP + 64;
+	       2 * (size_t)T2_NP + 16 + (size_t)(T2_THREADS / 32) * 16 * 4 + 5 * (size_t)T2_LANE_NE * 8 + 64;
 }
 
 #endif
