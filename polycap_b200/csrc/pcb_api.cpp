@@ -21,6 +21,7 @@
 #include <ctime>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "optconst.h"
@@ -34,6 +35,14 @@ extern "C" void pcb_energy_constants(size_t n_energies, const double *energies, 
 static std::mutex g_gpu_mutex; /* the device objects below are not re-entrant; calls are serialised */
 
 static bool quiet() { return getenv("POLYCAP_B200_QUIET") != NULL; }
+/* POLYCAP_B200_PHASES=1: wall-clock phases of polycap_source_get_transmission_efficiencies on stderr (tuning aid) */
+static bool phases_on() { return getenv("POLYCAP_B200_PHASES") != NULL; }
+static double now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 /* ------------------------------------------------------------------ optic cache
  * A device optic = profile tables + per-energy constants.  polycap_photon_launch is called once
@@ -574,26 +583,28 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	const int64_t want = n_photons;
 
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	const double t_begin = now_ms();
 	pcb_gpu_optic *g = optic_for(d, nE, source->energies, NULL, NULL, -1, error, WHO);
 	if (!g)
 		return NULL;
 	const int dev = pcb_gpu_optic_device(g);
 	const uint64_t seed = run_seed();
 	const pcb_source_desc sd = source_desc(source);
+	const double t_optic = now_ms();
 
-	double *d_sum = (double *)pcb_gpu_malloc(dev, nE * 8);
-	int64_t *d_cnt = (int64_t *)pcb_gpu_malloc(dev, PCB_C_COUNT * 8);
-	double *d_rf = (double *)pcb_gpu_malloc(dev, (size_t)want * 17 * 8);
-	double *d_rw = (double *)pcb_gpu_malloc(dev, (size_t)want * nE * 8);
+	/* tallies and exit records live in one device buffer kept with the optic (no cudaMalloc / cudaFree per call) */
+	auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+	const size_t o_cnt = up256(nE * 8), o_rf = o_cnt + up256(PCB_C_COUNT * 8), o_rw = o_rf + up256((size_t)want * 17 * 8),
+		     res_bytes = o_rw + up256((size_t)want * nE * 8);
+	char *d_res = (char *)pcb_gpu_optic_result(g, res_bytes);
+	double *d_sum = (double *)d_res;
+	int64_t *d_cnt = (int64_t *)(d_res + o_cnt);
+	double *d_rf = (double *)(d_res + o_rf);
+	double *d_rw = (double *)(d_res + o_rw);
 	std::vector<double> leak_all; /* concatenated leak records of counted photons */
 	int64_t n_leak_all = 0;
-	auto cleanup = [&]() {
-		pcb_gpu_free(dev, d_sum);
-		pcb_gpu_free(dev, d_cnt);
-		pcb_gpu_free(dev, d_rf);
-		pcb_gpu_free(dev, d_rw);
-	};
-	if (!d_sum || !d_cnt || !d_rf || !d_rw) {
+	auto cleanup = [&]() {};
+	if (!d_res) {
 		polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate device memory for %d exit records -> %s", WHO, n_photons, pcb_gpu_last_error());
 		cleanup();
 		return NULL;
@@ -606,10 +617,25 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	int64_t have = 0, next_id = 0, waves = 0;
 	const int64_t wave_bytes_per_id = 160 + 8 * (int64_t)nE;
 	const int64_t wave_max = std::max<int64_t>(4096, std::min<int64_t>((int64_t)1 << 24, ((int64_t)6 << 30) / wave_bytes_per_id));
-	double exit_frac = 0.5;
+	/* Wave size: ids needed at the exit fraction seen so far plus three standard deviations of that estimate and of the
+	 * count itself (ids past the want-th exit are traced and discarded).  The first wave of a call uses the fraction the
+	 * previous call with the same source geometry ended with; without one it is a probe of 2*need ids. */
+	uint64_t src_key = 1469598103934665603ULL;
+	for (size_t i = 0; i < sizeof sd; i++)
+		src_key = (src_key ^ ((const unsigned char *)&sd)[i]) * 1099511628211ULL;
+	int64_t est_exits = 0;
+	double exit_frac = pcb_gpu_optic_hint(g, src_key, &est_exits);
+	const double t_alloc = now_ms();
 	while (have < want) {
+		const double t_w0 = now_ms();
 		int64_t need = want - have;
-		int64_t n_ids = (int64_t)((double)need / exit_frac * 1.05) + 1024;
+		int64_t n_ids;
+		if (exit_frac > 0) {
+			const double margin = std::min(0.25, 3.0 * sqrt(1.0 / (double)std::max<int64_t>(est_exits, 1) + 1.0 / (double)need) + 0.002);
+			n_ids = (int64_t)((double)need / exit_frac * (1.0 + margin)) + 256;
+		} else {
+			n_ids = 2 * need + 1024;
+		}
 		if (n_ids > wave_max)
 			n_ids = wave_max;
 		int64_t used = 0, got = 0;
@@ -635,6 +661,10 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		have += got;
 		waves++;
 		exit_frac = std::max(1e-4, (double)have / (double)next_id);
+		est_exits = have;
+		if (phases_on())
+			fprintf(stderr, "polycap-b200 phases: wave %" PRId64 ": %" PRId64 " ids launched, %" PRId64 " used, %" PRId64 " exits, %.2f ms\n", waves, n_ids, used, got,
+				now_ms() - t_w0);
 		if (waves > 100000 || (next_id > ((int64_t)1 << 26) && have == 0)) {
 			polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: no photon reaches the exit window (%" PRId64 " started)", WHO, next_id);
 			cleanup();
@@ -642,6 +672,8 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		}
 	}
 
+	pcb_gpu_optic_set_hint(g, src_key, (double)have / (double)next_id, have);
+	const double t_waves = now_ms();
 	std::vector<double> sum(nE);
 	int64_t cnt[PCB_C_COUNT];
 	polycap_transmission_efficiencies *eff = (polycap_transmission_efficiencies *)calloc(1, sizeof(*eff));
@@ -660,8 +692,18 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		polycap_transmission_efficiencies_free(eff);
 		return NULL;
 	}
+	const double t_d2h = now_ms();
 	const double *rf = stage;
-	memcpy(im->exit_coord_weights, stage + (size_t)want * 17, rw_bytes);
+	/* staging -> caller-owned arrays: first-touch page faults dominate, so large results are unpacked by a few threads */
+	const int n_unpack = (rf_bytes + rw_bytes) > ((size_t)8 << 20) ? 4 : 1;
+	std::vector<std::thread> unpackers;
+	auto unpack_weights = [&](int part) {
+		const size_t lo = rw_bytes / 8 * (size_t)part / n_unpack, hi = rw_bytes / 8 * (size_t)(part + 1) / n_unpack;
+		memcpy(im->exit_coord_weights + lo, stage + (size_t)want * 17 + lo, (hi - lo) * 8);
+	};
+	for (int part = 1; part < n_unpack; part++)
+		unpackers.emplace_back(unpack_weights, part);
+	unpack_weights(0);
 	/* unpack the 17 record fields (struct _polycap_images, private.h:156-181) */
 	double **dst[16] = {&im->src_start_coords[0], &im->src_start_coords[1], &im->pc_start_coords[0], &im->pc_start_coords[1], &im->pc_start_dir[0],
 			    &im->pc_start_dir[1], &im->pc_start_elecv[0], &im->pc_start_elecv[1], &im->pc_exit_coords[0], &im->pc_exit_coords[1],
@@ -674,7 +716,12 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	im->pc_exit_nrefl = (int64_t *)malloc(sizeof(int64_t) * (size_t)want);
 	for (int64_t i = 0; i < want; i++)
 		im->pc_exit_nrefl[i] = (int64_t)rf[(size_t)15 * want + i];
+	for (auto &t : unpackers)
+		t.join();
 
+	if (phases_on())
+		fprintf(stderr, "polycap-b200 phases: optic %.2f ms, device buffers %.2f ms, waves %.2f ms, device->host %.2f ms, host unpack %.2f ms\n", t_optic - t_begin,
+			t_alloc - t_optic, t_waves - t_alloc, t_d2h - t_waves, now_ms() - t_d2h);
 	/* leak records (source.c:799-879, 982-1031) */
 	if (leak_calc) {
 		const size_t stride = 11 + nE;

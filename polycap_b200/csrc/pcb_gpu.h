@@ -59,6 +59,9 @@ void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl, int thr_ne
 int pcb_gpu_optic_reupload(pcb_gpu_optic *g, void *stream);
 size_t pcb_gpu_optic_input_bytes(const pcb_gpu_optic *g);
 void *pcb_gpu_optic_stage(pcb_gpu_optic *g, size_t bytes);
+void *pcb_gpu_optic_result(pcb_gpu_optic *g, size_t bytes);
+double pcb_gpu_optic_hint(const pcb_gpu_optic *g, uint64_t key, int64_t *exits);
+void pcb_gpu_optic_set_hint(pcb_gpu_optic *g, uint64_t key, double frac, int64_t exits);
 
 /* instrumentation (bench.py): CUDA-event timing of the trace kernels, kernel-launch counts */
 void pcb_gpu_optic_timing(pcb_gpu_optic *g, int on);

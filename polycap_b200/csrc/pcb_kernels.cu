@@ -76,6 +76,11 @@ struct pcb_gpu_optic {
 	size_t ec_bytes = 0;
 	void *h_stage = nullptr;
 	size_t h_stage_bytes = 0;
+	void *d_result = nullptr; /* exit records + tallies of one polycap_source_get_transmission_efficiencies call (grow-only) */
+	size_t d_result_bytes = 0;
+	uint64_t hint_key = 0; /* exit fraction seen by the last call with this source geometry: sizes the first wave of the next */
+	double hint_frac = 0;
+	int64_t hint_exits = 0;
 	double cap0 = 0, ext0 = 0;
 	/* wave buffers (grown on demand) */
 	int64_t wave_cap = 0;
@@ -255,6 +260,7 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	cudaFreeHost(g->h_tables);
 	cudaFreeHost(g->h_ec);
 	cudaFreeHost(g->h_stage);
+	cudaFree(g->d_result);
 	for (auto &p : g->ev_pending) {
 		cudaEventDestroy(p.first);
 		cudaEventDestroy(p.second);
@@ -291,6 +297,39 @@ extern "C" void *pcb_gpu_optic_stage(pcb_gpu_optic *g, size_t bytes)
 	}
 	g->h_stage_bytes = bytes;
 	return g->h_stage;
+}
+
+/* device memory for the results of one call, kept with the optic so that repeated calls do not cudaMalloc / cudaFree */
+extern "C" void *pcb_gpu_optic_result(pcb_gpu_optic *g, size_t bytes)
+{
+	if (bytes <= g->d_result_bytes)
+		return g->d_result;
+	cudaSetDevice(g->device);
+	cudaFree(g->d_result);
+	g->d_result = nullptr;
+	g->d_result_bytes = 0;
+	if (cudaMalloc(&g->d_result, bytes) != cudaSuccess) {
+		g_last_error = "cudaMalloc failed for the exit records";
+		g->d_result = nullptr;
+		return nullptr;
+	}
+	g->d_result_bytes = bytes;
+	return g->d_result;
+}
+
+extern "C" double pcb_gpu_optic_hint(const pcb_gpu_optic *g, uint64_t key, int64_t *exits)
+{
+	if (g->hint_key != key || g->hint_exits <= 0)
+		return 0.0;
+	if (exits)
+		*exits = g->hint_exits;
+	return g->hint_frac;
+}
+extern "C" void pcb_gpu_optic_set_hint(pcb_gpu_optic *g, uint64_t key, double frac, int64_t exits)
+{
+	g->hint_key = key;
+	g->hint_frac = frac;
+	g->hint_exits = exits;
 }
 
 /* ---- instrumentation ---- */

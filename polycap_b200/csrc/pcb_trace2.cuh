@@ -32,12 +32,18 @@
 #define T2_NP 1152 /* photon slots per CTA */
 #endif
 #define T2_QCAP 2048 /* ring capacity, power of two > T2_NP */
+#ifndef T2_LOCKSTEP
+#define T2_LOCKSTEP 0 /* 1: barrier-separated rounds with a deterministic batch assignment; 0: every warp claims work on its own */
+#endif
+#ifndef T2_CONSENSUS
+#define T2_CONSENSUS 1 /* the warps of a CTA prefer the same long task (see the claim code); 0: fullest queue wins every time */
+#endif
 #ifndef T2_LANE_NE
 #define T2_LANE_NE 32 /* up to this many energies a lane walks its own photon's weight vector; above, pairs are dealt over the warp */
 #endif
 #define T2_EMPTY 0xFFFFu
 
-enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_DONE, TQ_N };
+enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_REFL, TQ_DONE, TQ_N };
 
 /* flag bits of a photon slot */
 enum { F_SLOW = 1, F_DEEP = 2, F_WINIT = 4, F_INCUR = 8, F_INNXT = 16 };
@@ -56,7 +62,7 @@ struct T2Shared { /* pointers into dynamic shared memory */
 	__device__ __forceinline__ volatile unsigned short *q(int k) const { return qbase + k * T2_QCAP; }
 };
 
-enum { D_EX = 0, D_EY, D_EZ, D_DX, D_DY, D_DZ, D_VX, D_VY, D_VZ, D_LHX, D_LHY, D_LHZ, D_DTRAV, D_A, D_B, D_AUX, D_N };
+enum { D_EX = 0, D_EY, D_EZ, D_DX, D_DY, D_DZ, D_VX, D_VY, D_VZ, D_G0, D_G1, D_LHZ, D_DTRAV, D_A, D_B, D_AUX, D_N };
 
 __device__ __forceinline__ void t2_push(volatile unsigned short *buf, unsigned *tail, unsigned slot)
 {
@@ -73,7 +79,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	__shared__ __align__(8) uint64_t tma_bar;
 	__shared__ unsigned q_head[TQ_N], q_tail[TQ_N];
-	__shared__ int live;
+	__shared__ int live, cur;
+#if T2_LOCKSTEP
+	__shared__ unsigned snap_h[TQ_N], snap_c[TQ_N];
+#endif
 
 	const PcbOptic &o = P.o;
 	const int nmax = o.nmax;
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		}
 		q_tail[TQ_NEW] = T2_NP; /* every slot starts free */
 		live = T2_NP;
+		cur = TQ_HIT;
 	}
 	for (int i = threadIdx.x; i < T2_NP; i += blockDim.x)
 		S.q(TQ_NEW)[i] = (unsigned short)i;
@@ -154,8 +164,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	/* work and scheduler counters live in shared memory, one row per warp, updated by lane 0 (they would cost 12 registers) */
 	enum { W_STEPS = 0, W_SOLVES, W_REFL, W_LAUNCH, W_BATCHES, W_LANES, W_EMPTY, W_LOST, W_HIT_B, W_HIT_L, W_SCAN_B, W_SCAN_L, W_N = 16 };
 	volatile unsigned *wst = wstat + warp * W_N;
+#if !T2_LOCKSTEP
 	volatile unsigned *vhead = q_head, *vtail = q_tail;
-	volatile int *vlive = &live;
+	volatile int *vlive = &live, *vcur = &cur;
+#endif
 
 	/* begin one capil_trace call for the photon in registers (capil.c:1236-1246); see pcb_trace.cuh::trace_begin */
 #define T2_TRACE_BEGIN(on_wall)                                                                                       \
@@ -223,6 +235,91 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		flags = (flags & ~F_INCUR) | (in_cur_ ? F_INCUR : 0);                                                 \
 	} while (0)
 
+#if T2_LOCKSTEP
+	/* ---------------- rounds: between two CTA barriers no warp holds a photon, so every photon of the pool is queued.  All warps
+	 * read the same queue counts and each takes the batch its warp index selects from one ordering (full batches of wall hits
+	 * first), so nothing is raced for and the warps of the SM walk through the same task code at the same time: the instruction
+	 * working set at any moment is a window of one task, not twenty unrelated places of a 150 KB kernel. ---------------- */
+	for (;;) {
+		int type = -1, n = 0;
+		unsigned base = 0;
+		__syncthreads(); /* the pushes of the previous round are complete and visible */
+		if (threadIdx.x < TQ_N) {
+			snap_h[threadIdx.x] = q_head[threadIdx.x];
+			snap_c[threadIdx.x] = q_tail[threadIdx.x] - q_head[threadIdx.x];
+		}
+		__syncthreads();
+		{
+			const unsigned order_full = TQ_REFL | (TQ_HIT << 4) | (TQ_SCAN << 8) | (TQ_DONE << 12) | (TQ_NEW << 16); /* nibble k = k-th choice */
+			const unsigned order_part = TQ_DONE | (TQ_NEW << 4) | (TQ_SCAN << 8) | (TQ_HIT << 12) | (TQ_REFL << 16);
+			if (snap_c[0] + snap_c[1] + snap_c[2] + snap_c[3] + snap_c[4] == 0)
+				break; /* nothing queued, so nothing alive */
+			int idx = warp;
+#pragma unroll
+			for (int k = 0; k < TQ_N; k++) { /* full batches in priority order */
+				const int qk = (order_full >> (4 * k)) & 15;
+				const int f = (int)(snap_c[qk] >> 5);
+				if (type < 0) {
+					if (idx < f) {
+						type = qk;
+						base = snap_h[qk] + 32u * idx;
+						n = 32;
+					} else {
+						idx -= f;
+					}
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < TQ_N; k++) { /* then the partial ones: recycle slots first */
+				const int qk = (order_part >> (4 * k)) & 15;
+				const unsigned c = snap_c[qk];
+				if (type < 0 && (c & 31u)) {
+					if (idx == 0) {
+						type = qk;
+						base = snap_h[qk] + (c & ~31u);
+						n = (int)(c & 31u);
+					}
+					idx--;
+				}
+			}
+			if (threadIdx.x == 0) { /* advance the heads by what the T2_THREADS/32 warps of this round take */
+				int left = T2_THREADS / 32;
+#pragma unroll
+				for (int k = 0; k < TQ_N; k++) {
+					const int qk = (order_full >> (4 * k)) & 15;
+					const int f = (int)(snap_c[qk] >> 5);
+					const int t = f < left ? f : left;
+					left -= t;
+					q_head[qk] += 32u * t;
+				}
+#pragma unroll
+				for (int k = 0; k < TQ_N; k++) {
+					const int qk = (order_part >> (4 * k)) & 15;
+					const unsigned c = snap_c[qk];
+					if (left > 0 && (c & 31u)) {
+						q_head[qk] += c & 31u;
+						left--;
+					}
+				}
+			}
+			if (type < 0) {
+				if (lane == 0)
+					wst[W_EMPTY]++;
+				continue; /* fewer batches than warps in this round */
+			}
+		}
+		if (lane == 0) {
+			wst[W_BATCHES]++;
+			wst[W_LANES] += n;
+			if (type == TQ_HIT) { wst[W_HIT_B]++; wst[W_HIT_L] += n; wst[W_SOLVES] += n; }
+			if (type == TQ_SCAN) { wst[W_SCAN_B]++; wst[W_SCAN_L] += n; }
+		}
+		unsigned t_steps = 0; /* this lane's segment steps, reflections (<< 16) and launches (<< 24) in this task */
+		const bool act = lane < n;
+		unsigned slot = 0;
+		if (act)
+			slot = S.q(type)[(base + lane) & (T2_QCAP - 1)];
+#else
 	unsigned backoff = 256u;
 	for (;;) {
 		/* ---------------- claim a batch: lane k polls queue k, the fullest-first rule is evaluated by ballot ---------------- */
@@ -232,20 +329,32 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			unsigned cnt = 0;
 			if (lane < TQ_N)
 				cnt = vtail[lane] - vhead[lane];
-			/* priority: a full batch of wall hits, then of finished photons, long scans, free slots; else whatever is fullest */
+			/* Task choice.  The two long tasks (HIT: the solve, REFL: the reflection) are the kernel's hot code, ~20 KB of
+			 * instructions each; with every warp free to run either, twenty warps roam over more code than the SM's
+			 * instruction cache holds and the GPC-level cache that backs it saturates (ncu: 70 % hit rate, gcc instruction
+			 * requests at 85 % of peak).  So the warps follow a common preference `cur`: whoever finds its queue short of a
+			 * full batch moves the preference to the fullest queue.  The pool then flows through one task at a time, the
+			 * SM's working set is one task's code, and no barrier is needed.  The short tasks (DONE, NEW, SCAN: slot
+			 * recycling) run whenever they have a full batch. */
 			const unsigned full = __ballot_sync(0xffffffffu, cnt >= 32u);
 			const unsigned any = __ballot_sync(0xffffffffu, cnt > 0u);
-			/* a full batch of wall hits first (then long scans, finished photons, free slots); without any full batch, recycle
-			 * slots first (DONE, NEW: cheap, and they put more photons in flight) and take a partial HIT batch last */
-			const unsigned order_full = TQ_HIT | (TQ_SCAN << 4) | (TQ_DONE << 8) | (TQ_NEW << 12); /* nibble k = k-th choice */
-			const unsigned order_any = TQ_DONE | (TQ_NEW << 4) | (TQ_SCAN << 8) | (TQ_HIT << 12);
-			const unsigned pick = full ? full : any;
+			const unsigned pick = any;
 			if (pick) {
-#pragma unroll
-				for (int k = TQ_N - 1; k >= 0; k--) {
-					const int qk = ((full ? order_full : order_any) >> (4 * k)) & 15;
-					if (pick & (1u << qk))
-						type = qk;
+				const unsigned shortq = full & ((1u << TQ_DONE) | (1u << TQ_NEW) | (1u << TQ_SCAN));
+				const int c = *vcur;
+				if (shortq & (1u << TQ_DONE))
+					type = TQ_DONE;
+				else if (shortq & (1u << TQ_NEW))
+					type = TQ_NEW;
+				else if (shortq & (1u << TQ_SCAN))
+					type = TQ_SCAN;
+				else if (T2_CONSENSUS && (full & (1u << c)))
+					type = c;
+				else {
+					const unsigned key = __reduce_max_sync(0xffffffffu, lane < TQ_N ? ((cnt << 3) | (unsigned)lane) : 0u);
+					type = (int)(key & 7u);
+					if (lane == 0 && type != c && (type == TQ_HIT || type == TQ_REFL))
+						*vcur = type;
 				}
 				if (lane == 0) {
 					const unsigned h = vhead[type];
@@ -296,6 +405,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		}
 		__threadfence_block();
 
+#endif
+
 		/* Photon fields are read from the slot when a phase needs them and written back as soon as they are final, so that
 		 * few of them are live at any point (96 registers per thread, 640 threads). */
 #define SD(k) S.d[k][slot]
@@ -314,19 +425,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					S.code[slot] = (signed char)code;
 			}
 		} else if (type == TQ_HIT) {
-			/* ---------------- HIT: solve the candidate segment (capil.c:1256-1309); on a hit the reflection: travel and in-optic
-			 * checks (capil.c:1315-1343), capil_reflect preamble + geometry, the energy loop, the specular direction and the
-			 * start of the next capil_trace call; then scan on to the next candidate ---------------- */
-			bool hitting = false;
-			double dx = 0, dy = 0, dz = 1, snx = 0, sny = 0, snz = 0, cosalfa = 0; /* live through the energy loop */
-			double g_ct = 0, g_st = 0, g_fs = 0, alfa = 0;
-			unsigned flags = 0;
-			int iseg = 0, ix = 0, code = 0;
+			/* ---------------- HIT: solve the candidate segment (capil.c:1256-1309); on a hit the travel and in-optic checks
+			 * (capil.c:1315-1343) and on to the reflection task; without one, scan on to the next candidate ---------------- */
 			if (act) {
-				flags = S.flags[slot];
-				iseg = S.iseg[slot];
+				bool hitting = false;
+				double snx = 0, sny = 0, snz = 0, cosalfa = 0;
+				unsigned flags = S.flags[slot];
+				int iseg = S.iseg[slot], ix = 0, code = 0;
 				double ex = SD(D_EX), ey = SD(D_EY), ez = SD(D_EZ);
-				dx = SD(D_DX); dy = SD(D_DY); dz = SD(D_DZ);
+				const double dx = SD(D_DX), dy = SD(D_DY), dz = SD(D_DZ);
 				const double A = SD(D_A), B = SD(D_B);
 				const bool slow = flags & F_SLOW;
 				const int i = iseg;
@@ -420,7 +527,34 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						}
 					}
 				}
-				if (hitting) { /* capil_reflect preamble, capil.c:596-602, and the energy-independent geometry */
+				if (hitting) { /* the wall normal goes to the reflection task through the slot */
+					SD(D_G0) = snx; SD(D_G1) = sny; SD(D_AUX) = snz;
+					S.ix[slot] = ix;
+					next = TQ_REFL;
+				}
+				S.iseg[slot] = iseg;
+				S.flags[slot] = (unsigned char)flags;
+				S.code[slot] = (signed char)code;
+			}
+		} else if (type == TQ_REFL) {
+			/* ---------------- REFL: capil_reflect (capil.c:596-645) for a photon on the wall: preamble + geometry, the energy
+			 * loop, the specular direction and the start of the next capil_trace call; then the scan to the next candidate ---------------- */
+			bool hitting = act;
+			double dx = 0, dy = 0, dz = 1, snx = 0, sny = 0, snz = 0, cosalfa = 0; /* live through the energy loop */
+			double g_ct = 0, g_st = 0, g_fs = 0, alfa = 0;
+			unsigned flags = 0;
+			int iseg = 0, ix = 0, code = 0;
+			if (act) {
+				flags = S.flags[slot];
+				iseg = S.iseg[slot];
+				ix = S.ix[slot];
+				dx = SD(D_DX); dy = SD(D_DY); dz = SD(D_DZ);
+				snx = SD(D_G0); sny = SD(D_G1); snz = SD(D_AUX);
+				{
+					const V3 sn0 = {snx, sny, snz}, pd = {dx, dy, dz};
+					cosalfa = dot3(sn0, pd); /* the same product the solve task tested */
+				}
+				{ /* capil_reflect preamble, capil.c:596-602, and the energy-independent geometry */
 					V3 sn = {snx, sny, snz};
 					norm3(sn);
 					V3 d = {dx, dy, dz};
@@ -495,7 +629,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				const unsigned go = __ballot_sync(0xffffffffu, hitting);
 				const int n_go = __popc(go);
 				if (hitting) {
-					SD(D_LHX) = g_ct; SD(D_LHY) = g_st; SD(D_LHZ) = g_fs; SD(D_AUX) = alfa;
+					SD(D_G0) = g_ct; SD(D_G1) = g_st; SD(D_LHZ) = g_fs; SD(D_AUX) = alfa;
 					batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
 					if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
 						double *w0 = wcta + (unsigned long long)slot * nE;
@@ -532,7 +666,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 #pragma unroll
 						for (int u = 0; u < U; u++)
 							r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
-										 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_LHX][sl[u]], S.d[D_LHY][sl[u]], S.d[D_LHZ][sl[u]],
+										 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_G0][sl[u]], S.d[D_G1][sl[u]], S.d[D_LHZ][sl[u]],
 										 1. - S.d[D_LHZ][sl[u]]);
 #pragma unroll
 						for (int u = 0; u < U; u++) {
@@ -561,7 +695,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						double w = *wp;
 						const double n_re = __ldg(ec + EC_NRE * nE + e), n_im = __ldg(ec + EC_NIM * nE + e);
 						const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
-						const double c_t = S.d[D_LHX][sl], s_t = S.d[D_LHY][sl], f_s = S.d[D_LHZ][sl];
+						const double c_t = S.d[D_G0][sl], s_t = S.d[D_G1][sl], f_s = S.d[D_LHZ][sl];
 						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s)
 									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s);
 						if (rough) {
@@ -809,6 +943,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		}
 
 		/* ---------------- hand the photons on: one tail reservation per warp and target queue ---------------- */
+#if T2_LOCKSTEP
+#pragma unroll
+		for (int qk = 0; qk < TQ_N; qk++) {
+			const unsigned mq = __ballot_sync(0xffffffffu, act && next == qk);
+			if (mq) {
+				unsigned tb0 = 0;
+				const int leader = __ffs(mq) - 1;
+				if (lane == leader)
+					tb0 = atomicAdd(&q_tail[qk], (unsigned)__popc(mq));
+				tb0 = __shfl_sync(0xffffffffu, tb0, leader);
+				if (act && next == qk)
+					S.q(qk)[(tb0 + __popc(mq & ((1u << lane) - 1u))) & (T2_QCAP - 1)] = (unsigned short)slot;
+			}
+		}
+	}
+#else
 		__threadfence_block(); /* the slots' state is visible before their ids are */
 #pragma unroll
 		for (int qk = 0; qk < TQ_N; qk++) {
@@ -828,6 +978,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			}
 		}
 	}
+#endif
 #undef T2_SCAN_STEPS
 #undef T2_TRACE_BEGIN
 
