@@ -1059,6 +1059,8 @@ __global__ void div_selftest_kernel(unsigned long long n, unsigned long long see
 				bits &= 0xfff0000000000000ULL; /* powers of two, zeros, infinities */
 			if ((sel >> 28) == 1)
 				bits |= 0x000fffffffffffffULL; /* all-ones significands */
+			if (k == 0 && (sel >> 28) == 2)
+				bits &= 0x8000000000000000ULL; /* zero numerators of either sign */
 			v[k] = __longlong_as_double((long long)bits);
 		}
 		const PcbDivisor d = pcb_divisor(v[1]);

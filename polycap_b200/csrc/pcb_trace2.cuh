@@ -496,10 +496,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						if (outside) {
 							code = -1;
 							next = TQ_DONE;
-						} else { /* no wall hit in this segment: on to the next candidate while the photon is in registers */
+						} else { /* no wall hit in this segment (1 solve in 20): the scan task finds the next candidate */
 							iseg = i + 1;
 							flags = (flags & ~F_INCUR) | ((flags & F_INNXT) ? F_INCUR : 0);
-							T2_SCAN_STEPS(24);
+							next = TQ_SCAN;
 						}
 					}
 				}
@@ -960,10 +960,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	}
 #else
 		__threadfence_block(); /* the slots' state is visible before their ids are */
-#pragma unroll
-		for (int qk = 0; qk < TQ_N; qk++) {
-			const unsigned mq = __ballot_sync(0xffffffffu, act && next == qk);
-			if (mq) {
+		{
+			unsigned todo = __ballot_sync(0xffffffffu, act && next >= 0);
+			while (todo) { /* one pass per target queue present in the batch */
+				const int qk = __shfl_sync(0xffffffffu, next, __ffs(todo) - 1);
+				const unsigned mq = __ballot_sync(0xffffffffu, act && next == qk);
 				unsigned tb0 = 0;
 				const int leader = __ffs(mq) - 1;
 				if (lane == leader)
@@ -975,6 +976,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					}
 					*e = (unsigned short)slot;
 				}
+				todo &= ~mq;
 			}
 		}
 	}
