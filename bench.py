@@ -299,12 +299,15 @@ def main():
         os.environ["POLYCAP_B200_REUPLOAD"] = "1"
         os.environ["POLYCAP_B200_SEED"] = "777"
         with quiet_stdout():
-            src.get_transmission_efficiencies(-1, max(1000, n_exit // 10))  # warm-up of the API path
+            src.get_transmission_efficiencies(-1, n_exit)  # warm-up of the API path at full size (buffers, first-wave estimate)
             barrier()
             t0 = time.perf_counter()
-            reps = max(1, min(args.steps, 3))
+            reps = max(1, min(args.steps, 5))
+            per_call = []
             for _ in range(reps):
+                tc = time.perf_counter()
                 e2e_last = src.get_transmission_efficiencies(-1, n_exit)
+                per_call.append(time.perf_counter() - tc)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         # simulated photons: i_start of the result object (same seed => every call simulates the same photons)
@@ -325,7 +328,7 @@ def main():
                "h2d_bytes_per_step": int(5 * 8 * 1002 + 6 * 8 * nE), "d2h_bytes_per_step": int(n_exit * 8 * (17 + nE) + 8 * nE + 8 * pc.N_COUNTERS),
                "call": "polycap_source_get_transmission_efficiencies(source, -1, n_photons=%d exits) x %d, tables + per-energy constants re-sent from pinned host memory per call "
                        "(POLYCAP_B200_REUPLOAD), exit records returned in host arrays" % (n_exit, reps),
-               "simulated_photons_per_call": int(i_start), "seconds": float(t_e2e.item())}
+               "simulated_photons_per_call": int(i_start), "seconds": float(t_e2e.item()), "seconds_per_call": [round(t, 4) for t in per_call]}
         del os.environ["POLYCAP_B200_REUPLOAD"]
 
     if rank == 0:
@@ -346,7 +349,7 @@ def main():
             "counters": cnt, "efficiencies": (sw / max(photons, 1)).tolist(),
             "gpu_launches": int(kernels[0] - k0_kernels[0]), "trace_kernel_launches": int(trace_launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak if dfma_peak > 0 else None,
-                         "traffic": None, "kernel": "pcb_trace_kernel<MODE_SOURCE>", "kernel_ms_per_launch": 1e3 * trace_s / max(trace_launches, 1),
+                         "traffic": None, "kernel": ("pcb_trace_kernel" if os.environ.get("POLYCAP_B200_KERNEL") == "1" else "pcb_trace2_kernel") + "<MODE_SOURCE, cheap weights>", "kernel_ms_per_launch": 1e3 * trace_s / max(trace_launches, 1),
                          "kernel_share_of_step": trace_s / total_s if total_s > 0 else None,
                          "algorithmic_flops_per_launch": flops / world / max(trace_launches, 1),
                          "model": "155*launched + 24*seg_steps + 445*refl + 70*nE*refl + 100*exit (SURVEY 8d)",

@@ -682,10 +682,17 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	im->exit_coord_weights = (double *)malloc(sizeof(double) * (size_t)want * nE);
 	/* device -> pinned staging (one DMA per array at PCIe speed) -> the caller-owned arrays of struct _polycap_images */
 	const size_t rf_bytes = (size_t)want * 17 * 8, rw_bytes = (size_t)want * nE * 8;
+	const double t_h0 = now_ms();
 	double *stage = (double *)pcb_gpu_optic_stage(g, rf_bytes + rw_bytes);
+	const double t_h1 = now_ms();
 	bool ok = stage != NULL && pcb_gpu_copy_to_host(dev, sum.data(), d_sum, nE * 8, NULL) == 0 &&
-		  pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0 && pcb_gpu_copy_to_host(dev, stage, d_rf, rf_bytes, NULL) == 0 &&
-		  pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, d_rw, rw_bytes, NULL) == 0;
+		  pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0;
+	const double t_h2 = now_ms();
+	ok = ok && pcb_gpu_copy_to_host(dev, stage, d_rf, rf_bytes, NULL) == 0 &&
+	     pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, d_rw, rw_bytes, NULL) == 0;
+	if (phases_on())
+		fprintf(stderr, "polycap-b200 phases: result alloc %.2f ms, staging %.2f ms, tallies %.2f ms, records %.2f ms\n", t_h0 - t_waves, t_h1 - t_h0, t_h2 - t_h1,
+			now_ms() - t_h2);
 	cleanup();
 	if (!ok) {
 		gpu_fail(error, WHO);
@@ -709,13 +716,22 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 			    &im->pc_start_dir[1], &im->pc_start_elecv[0], &im->pc_start_elecv[1], &im->pc_exit_coords[0], &im->pc_exit_coords[1],
 			    &im->pc_exit_coords[2], &im->pc_exit_dir[0], &im->pc_exit_dir[1], &im->pc_exit_elecv[0], &im->pc_exit_elecv[1], &im->pc_exit_dtravel};
 	const int src_field[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16};
-	for (int f = 0; f < 16; f++) {
+	for (int f = 0; f < 16; f++)
 		*dst[f] = (double *)malloc(sizeof(double) * (size_t)want);
-		memcpy(*dst[f], rf + (size_t)src_field[f] * want, sizeof(double) * (size_t)want);
-	}
 	im->pc_exit_nrefl = (int64_t *)malloc(sizeof(int64_t) * (size_t)want);
-	for (int64_t i = 0; i < want; i++)
-		im->pc_exit_nrefl[i] = (int64_t)rf[(size_t)15 * want + i];
+	auto unpack_fields = [&](int part) {
+		for (int f = part; f < 16; f += n_unpack)
+			memcpy(*dst[f], rf + (size_t)src_field[f] * want, sizeof(double) * (size_t)want);
+		const int64_t lo = want * part / n_unpack, hi = want * (part + 1) / n_unpack;
+		for (int64_t i = lo; i < hi; i++)
+			im->pc_exit_nrefl[i] = (int64_t)rf[(size_t)15 * want + i];
+	};
+	for (auto &t : unpackers)
+		t.join();
+	unpackers.clear();
+	for (int part = 1; part < n_unpack; part++)
+		unpackers.emplace_back(unpack_fields, part);
+	unpack_fields(0);
 	for (auto &t : unpackers)
 		t.join();
 
