@@ -340,6 +340,15 @@ def main():
         rec_bytes = cnt["exit"] * 8 * (17 + nE) * 2 + cnt["ids"] * (1 + 4 + 8)  # dense exit records written + re-read by the tally; status/irefl/rank per id
         # per GPU: rank 0's trace time over rank 0's share of the work (weak scaling: equal shares)
         achieved_tf = flops / world / trace_s / 1e12 if trace_s > 0 else 0.0
+        # DRAM bytes per launch of the dominant kernel: per-id figure of the committed ncu capture x ids per launch (None without one)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+            if tr:
+                traffic = tr["dram_bytes_per_id"] * cnt["ids"] / world / max(trace_launches, 1)
+                traffic_src = "ncu dram bytes per photon id (%s) x ids per launch" % tr["capture"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": "photons/s", "value": photons / total_s, "unit": "photons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -349,7 +358,7 @@ def main():
             "counters": cnt, "efficiencies": (sw / max(photons, 1)).tolist(),
             "gpu_launches": int(kernels[0] - k0_kernels[0]), "trace_kernel_launches": int(trace_launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak if dfma_peak > 0 else None,
-                         "traffic": None, "kernel": ("pcb_trace_kernel" if os.environ.get("POLYCAP_B200_KERNEL") == "1" else "pcb_trace2_kernel") + "<MODE_SOURCE, cheap weights>", "kernel_ms_per_launch": 1e3 * trace_s / max(trace_launches, 1),
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": ("pcb_trace_kernel" if os.environ.get("POLYCAP_B200_KERNEL") == "1" else "pcb_trace2_kernel") + "<MODE_SOURCE, cheap weights>", "kernel_ms_per_launch": 1e3 * trace_s / max(trace_launches, 1),
                          "kernel_share_of_step": trace_s / total_s if total_s > 0 else None,
                          "algorithmic_flops_per_launch": flops / world / max(trace_launches, 1),
                          "model": "155*launched + 24*seg_steps + 445*refl + 70*nE*refl + 100*exit (SURVEY 8d)",

@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					if (ix < nmax && T.z[ix] <= ez) {
 						found = ix;
 					} else {
-						for (int j = ix - 1; j >= 0; j--)
+						_Pragma("unroll 1") for (int j = ix - 1; j >= 0; j--)
 							if (T.z[j] <= ez) {
 								found = j;
 								break;
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
 					if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
 						double *w0 = wcta + (unsigned long long)slot * nE;
-						for (int e2 = 0; e2 < nE; e2++)
+						_Pragma("unroll 2") for (int e2 = 0; e2 < nE; e2++)
 							w0[e2] = 1.0;
 					}
 				}
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				}
 				if (wr_rec || status == ST_ABSORBED) {
 					double *W = P.out.weights + (unsigned long long)lid * nE;
-					for (int e2 = 0; e2 < nE; e2++)
+					_Pragma("unroll 2") for (int e2 = 0; e2 < nE; e2++)
 						W[e2] = w_init ? wsl[e2] : 1.0;
 				}
 				next = TQ_NEW;
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					SD(D_VX) = s0.ev.x; SD(D_VY) = s0.ev.y; SD(D_VZ) = s0.ev.z;
 					int z_id = 0;
 					if (ez > 0) {
-						for (int i = 0; i < nmax; i++)
+						_Pragma("unroll 1") for (int i = 0; i < nmax; i++)
 							if (T.z[i] <= ez)
 								z_id = i;
 					}
@@ -836,12 +836,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						B = r_i * (3. / 2);
 						ix = 0;
 						if (ez > 0) {
-							for (int i = 0; i <= nmax; i++)
+							_Pragma("unroll 1") for (int i = 0; i <= nmax; i++)
 								if (T.z[i] <= ez)
 									ix = i;
 						} else if (T.z[0] <= ez) {
 							ix = 0;
-							for (int i = 1; i <= nmax && T.z[i] <= ez; i++)
+							_Pragma("unroll 1") for (int i = 1; i <= nmax && T.z[i] <= ez; i++)
 								ix = i;
 						}
 						double rad_here, cx_here, cy_here;
