@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					pi = pu[0];
 					e = eu[0];
 				}
-				for (; j0 < total; j0 += 32) {
+				_Pragma("unroll 1") for (; j0 < total; j0 += 32) {
 					if (j0 + lane < total) {
 						const unsigned sl = batch[pi];
 						double *wp = wcta + (unsigned long long)sl * nE + e;
