@@ -35,6 +35,9 @@
 #ifndef T2_LOCKSTEP
 #define T2_LOCKSTEP 0 /* 1: barrier-separated rounds with a deterministic batch assignment; 0: every warp claims work on its own */
 #endif
+#ifndef T2_STICKY
+#define T2_STICKY 0
+#endif
 #ifndef T2_CONSENSUS
 #define T2_CONSENSUS 1 /* the warps of a CTA prefer the same long task (see the claim code); 0: fullest queue wins every time */
 #endif
@@ -315,6 +318,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			slot = S.q(type)[(base + lane) & (T2_QCAP - 1)];
 #else
 	unsigned backoff = 256u;
+#if T2_STICKY
+	int last = -1;
+#endif
 	for (;;) {
 		/* ---------------- claim a batch: lane k polls queue k, the fullest-first rule is evaluated by ballot ---------------- */
 		int type = -1, n = 0;
@@ -342,6 +348,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					type = TQ_NEW;
 				else if (shortq & (1u << TQ_SCAN))
 					type = TQ_SCAN;
+#if T2_STICKY
+				else if (last >= 0 && (full & (1u << last)))
+					type = last; /* the code this warp ran last is the likeliest to be cached still */
+#endif
 				else if (T2_CONSENSUS && (full & (1u << c)))
 					type = c;
 				else {
@@ -380,6 +390,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			}
 		}
 		backoff = 256u;
+#if T2_STICKY
+		last = (type == TQ_HIT || type == TQ_REFL) ? type : last;
+#endif
 		if (lane == 0) {
 			wst[W_BATCHES]++;
 			wst[W_LANES] += n;
