@@ -519,6 +519,35 @@ class TransmissionEfficiencies:
     exit_arrays = property(lambda self: self._load_exit())
     start_arrays = property(lambda self: self._load_start())
 
+    @property
+    def records(self):
+        """Zero-copy numpy views of the result's own structure-of-arrays storage (struct _polycap_images,
+        src/polycap-private.h:156-181): no re-packing into vector arrays, no per-photon objects.  Read-only; the views keep this
+        object alive.  Keys are the struct's field names; two-/three-component fields are tuples of arrays."""
+        class _Images(C.Structure):
+            _fields_ = [("i_start", C.c_int64), ("i_exit", C.c_int64), ("src_start_coords", c_double_p * 2), ("pc_start_coords", c_double_p * 2),
+                        ("pc_start_dir", c_double_p * 2), ("pc_start_elecv", c_double_p * 2), ("pc_exit_coords", c_double_p * 3),
+                        ("pc_exit_dir", c_double_p * 2), ("pc_exit_elecv", c_double_p * 2), ("pc_exit_nrefl", c_int64_p),
+                        ("pc_exit_dtravel", c_double_p), ("exit_coord_weights", c_double_p)]
+
+        class _Te(C.Structure):
+            _fields_ = [("n_energies", C.c_size_t), ("energies", c_double_p), ("efficiencies", c_double_p), ("images", C.POINTER(_Images))]
+        te = C.cast(self._trans_eff, C.POINTER(_Te)).contents
+        im = te.images.contents
+        n, nE = int(im.i_exit), int(te.n_energies)
+
+        def view(ptr, shape):
+            a = np.ctypeslib.as_array(ptr, shape) if n else np.zeros(shape, dtype=np.int64 if ptr._type_ is C.c_int64 else np.float64)
+            a.flags.writeable = False
+            return a
+        out = {"i_start": int(im.i_start), "i_exit": n, "_owner": self}
+        for name, _ in _Images._fields_[2:9]:
+            out[name] = tuple(view(q, (n,)) for q in getattr(im, name))
+        out["pc_exit_nrefl"] = view(im.pc_exit_nrefl, (n,))
+        out["pc_exit_dtravel"] = view(im.pc_exit_dtravel, (n,))
+        out["exit_coord_weights"] = view(im.exit_coord_weights, (n, nE))
+        return out
+
 
 class Source:
     """polycap.pyx:1042-1152"""

@@ -257,6 +257,18 @@ def test_transmission_efficiencies_api(pc):
     assert st["n_start"] > 30000
     w0 = next(te.exit_weights)
     assert not w0.flags.writeable and w0.size == 7
+    # zero-copy views of the result's own storage (struct _polycap_images) agree with the re-packed getters
+    rec = te.records
+    assert rec["i_exit"] == 30000 and rec["i_start"] == st["n_start"]
+    for k in range(3):
+        assert np.array_equal(rec["pc_exit_coords"][k], ex["coords"][:, k])
+    for k in range(2):
+        assert np.array_equal(rec["pc_exit_dir"][k], ex["direction"][:, k])
+        assert np.array_equal(rec["pc_start_coords"][k], st["coords"][:, k])
+        assert np.array_equal(rec["src_start_coords"][k], st["src"][:, k])
+    assert np.array_equal(rec["pc_exit_nrefl"], ex["n_refl"]) and np.array_equal(rec["pc_exit_dtravel"], ex["d_travel"])
+    assert np.array_equal(rec["exit_coord_weights"], ex["weights"])
+    assert not rec["exit_coord_weights"].flags.writeable
 
 
 # ------------------------------------------------------------------ properties at larger sizes
