@@ -21,7 +21,6 @@
 #include <ctime>
 #include <algorithm>
 #include <mutex>
-#include <thread>
 #include <vector>
 
 #include "optconst.h"
@@ -558,6 +557,64 @@ static pcb_source_desc source_desc(const polycap_source *s)
 
 extern "C" void polycap_transmission_efficiencies_free(polycap_transmission_efficiencies *efficiencies);
 
+/* ---- result arenas.  The exit records of a call -- 16 double arrays, the reflection counts and the weight matrix of
+ * struct _polycap_images -- are slices of ONE pinned host block laid out like the device's record buffer, so the device
+ * copies straight into the arrays the caller reads: no staging copy, no first-touch page faults.  Pinning is slow
+ * (~1 GB/s), so blocks released by polycap_transmission_efficiencies_free are kept for the next call. */
+struct ResultArena {
+	void *p;
+	size_t bytes;
+	bool pinned;
+};
+static std::mutex g_arena_mutex;
+static std::vector<ResultArena> g_arena_pool;						/* released blocks, at most ARENA_KEEP */
+static std::vector<std::pair<const void *, ResultArena>> g_arena_of;			/* live results -> their block */
+enum { ARENA_KEEP = 3 };
+
+static ResultArena arena_take(size_t bytes)
+{
+	{
+		std::lock_guard<std::mutex> lk(g_arena_mutex);
+		int best = -1;
+		for (int i = 0; i < (int)g_arena_pool.size(); i++)
+			if (g_arena_pool[i].bytes >= bytes && g_arena_pool[i].bytes <= 4 * bytes + (1 << 20) &&
+			    (best < 0 || g_arena_pool[i].bytes < g_arena_pool[best].bytes))
+				best = i;
+		if (best >= 0) {
+			ResultArena a = g_arena_pool[best];
+			g_arena_pool.erase(g_arena_pool.begin() + best);
+			return a;
+		}
+	}
+	/* POLYCAP_B200_PAGEABLE_RESULTS=1: plain malloc (a one-shot caller with a multi-GB result does not pay for pinning) */
+	const bool pageable = getenv("POLYCAP_B200_PAGEABLE_RESULTS") != NULL;
+	ResultArena a = {pageable ? malloc(bytes) : pcb_gpu_host_alloc(bytes), bytes, !pageable};
+	return a;
+}
+
+static void arena_release(ResultArena a)
+{
+	ResultArena drop = {NULL, 0, false};
+	{
+		std::lock_guard<std::mutex> lk(g_arena_mutex);
+		g_arena_pool.push_back(a);
+		if (g_arena_pool.size() > ARENA_KEEP) { /* drop the smallest */
+			size_t k = 0;
+			for (size_t i = 1; i < g_arena_pool.size(); i++)
+				if (g_arena_pool[i].bytes < g_arena_pool[k].bytes)
+					k = i;
+			drop = g_arena_pool[k];
+			g_arena_pool.erase(g_arena_pool.begin() + k);
+		}
+	}
+	if (drop.p) {
+		if (drop.pinned)
+			pcb_gpu_host_free(drop.p);
+		else
+			free(drop.p);
+	}
+}
+
 extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_efficiencies(polycap_source *source, int max_threads, int n_photons,
 											    bool leak_calc, polycap_progress_monitor *progress_monitor,
 											    polycap_error **error)
@@ -679,11 +736,11 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	polycap_transmission_efficiencies *eff = (polycap_transmission_efficiencies *)calloc(1, sizeof(*eff));
 	eff->images = (struct _polycap_images *)calloc(1, sizeof(struct _polycap_images));
 	struct _polycap_images *im = eff->images;
-	im->exit_coord_weights = (double *)malloc(sizeof(double) * (size_t)want * nE);
-	/* device -> pinned staging (one DMA per array at PCIe speed) -> the caller-owned arrays of struct _polycap_images */
+	/* device -> the pinned block whose slices are the arrays of struct _polycap_images (one DMA per block at PCIe speed) */
 	const size_t rf_bytes = (size_t)want * 17 * 8, rw_bytes = (size_t)want * nE * 8;
 	const double t_h0 = now_ms();
-	double *stage = (double *)pcb_gpu_optic_stage(g, rf_bytes + rw_bytes);
+	const ResultArena arena = arena_take(rf_bytes + rw_bytes);
+	double *stage = (double *)arena.p;
 	const double t_h1 = now_ms();
 	bool ok = stage != NULL && pcb_gpu_copy_to_host(dev, sum.data(), d_sum, nE * 8, NULL) == 0 &&
 		  pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0;
@@ -691,52 +748,41 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	ok = ok && pcb_gpu_copy_to_host(dev, stage, d_rf, rf_bytes, NULL) == 0 &&
 	     pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, d_rw, rw_bytes, NULL) == 0;
 	if (phases_on())
-		fprintf(stderr, "polycap-b200 phases: result alloc %.2f ms, staging %.2f ms, tallies %.2f ms, records %.2f ms\n", t_h0 - t_waves, t_h1 - t_h0, t_h2 - t_h1,
+		fprintf(stderr, "polycap-b200 phases: result object %.2f ms, pinned block %.2f ms, tallies %.2f ms, records %.2f ms\n", t_h0 - t_waves, t_h1 - t_h0, t_h2 - t_h1,
 			now_ms() - t_h2);
 	cleanup();
 	if (!ok) {
-		gpu_fail(error, WHO);
+		if (stage == NULL)
+			polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate pinned host memory for %d exit records -> %s", WHO, n_photons, pcb_gpu_last_error());
+		else
+			gpu_fail(error, WHO);
+		if (arena.p)
+			arena_release(arena);
 		polycap_transmission_efficiencies_free(eff);
 		return NULL;
 	}
+	{
+		std::lock_guard<std::mutex> lk(g_arena_mutex);
+		g_arena_of.emplace_back((const void *)eff, arena);
+	}
 	const double t_d2h = now_ms();
-	const double *rf = stage;
-	/* staging -> caller-owned arrays: first-touch page faults dominate, so large results are unpacked by a few threads */
-	const int n_unpack = (rf_bytes + rw_bytes) > ((size_t)8 << 20) ? 4 : 1;
-	std::vector<std::thread> unpackers;
-	auto unpack_weights = [&](int part) {
-		const size_t lo = rw_bytes / 8 * (size_t)part / n_unpack, hi = rw_bytes / 8 * (size_t)(part + 1) / n_unpack;
-		memcpy(im->exit_coord_weights + lo, stage + (size_t)want * 17 + lo, (hi - lo) * 8);
-	};
-	for (int part = 1; part < n_unpack; part++)
-		unpackers.emplace_back(unpack_weights, part);
-	unpack_weights(0);
-	/* unpack the 17 record fields (struct _polycap_images, private.h:156-181) */
+	double *rf = stage;
+	/* the record fields of struct _polycap_images (private.h:156-181) in the device buffer's order; the reflection counts
+	 * arrive as doubles and are converted in place */
 	double **dst[16] = {&im->src_start_coords[0], &im->src_start_coords[1], &im->pc_start_coords[0], &im->pc_start_coords[1], &im->pc_start_dir[0],
 			    &im->pc_start_dir[1], &im->pc_start_elecv[0], &im->pc_start_elecv[1], &im->pc_exit_coords[0], &im->pc_exit_coords[1],
 			    &im->pc_exit_coords[2], &im->pc_exit_dir[0], &im->pc_exit_dir[1], &im->pc_exit_elecv[0], &im->pc_exit_elecv[1], &im->pc_exit_dtravel};
 	const int src_field[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16};
 	for (int f = 0; f < 16; f++)
-		*dst[f] = (double *)malloc(sizeof(double) * (size_t)want);
-	im->pc_exit_nrefl = (int64_t *)malloc(sizeof(int64_t) * (size_t)want);
-	auto unpack_fields = [&](int part) {
-		for (int f = part; f < 16; f += n_unpack)
-			memcpy(*dst[f], rf + (size_t)src_field[f] * want, sizeof(double) * (size_t)want);
-		const int64_t lo = want * part / n_unpack, hi = want * (part + 1) / n_unpack;
-		for (int64_t i = lo; i < hi; i++)
-			im->pc_exit_nrefl[i] = (int64_t)rf[(size_t)15 * want + i];
-	};
-	for (auto &t : unpackers)
-		t.join();
-	unpackers.clear();
-	for (int part = 1; part < n_unpack; part++)
-		unpackers.emplace_back(unpack_fields, part);
-	unpack_fields(0);
-	for (auto &t : unpackers)
-		t.join();
-
+		*dst[f] = rf + (size_t)src_field[f] * want;
+	im->exit_coord_weights = rf + (size_t)want * 17;
+	im->pc_exit_nrefl = (int64_t *)(rf + (size_t)15 * want);
+	for (int64_t i = 0; i < want; i++) {
+		const double v = rf[(size_t)15 * want + i];
+		im->pc_exit_nrefl[i] = (int64_t)v;
+	}
 	if (phases_on())
-		fprintf(stderr, "polycap-b200 phases: optic %.2f ms, device buffers %.2f ms, waves %.2f ms, device->host %.2f ms, host unpack %.2f ms\n", t_optic - t_begin,
+		fprintf(stderr, "polycap-b200 phases: optic %.2f ms, device buffers %.2f ms, waves %.2f ms, device->host %.2f ms, record pointers %.2f ms\n", t_optic - t_begin,
 			t_alloc - t_optic, t_waves - t_alloc, t_d2h - t_waves, now_ms() - t_d2h);
 	/* leak records (source.c:799-879, 982-1031) */
 	if (leak_calc) {
@@ -816,22 +862,41 @@ extern "C" void polycap_transmission_efficiencies_free(polycap_transmission_effi
 {
 	if (!eff)
 		return;
+	ResultArena arena = {NULL, 0, false};
+	{
+		std::lock_guard<std::mutex> lk(g_arena_mutex);
+		for (size_t i = 0; i < g_arena_of.size(); i++)
+			if (g_arena_of[i].first == (const void *)eff) {
+				arena = g_arena_of[i].second;
+				g_arena_of.erase(g_arena_of.begin() + i);
+				break;
+			}
+	}
 	free(eff->energies);
 	free(eff->efficiencies);
 	if (eff->images) {
 		struct _polycap_images *im = eff->images;
+		if (!arena.p) { /* exit records are slices of the arena otherwise */
+			for (int k = 0; k < 2; k++) {
+				free(im->src_start_coords[k]); free(im->pc_start_coords[k]); free(im->pc_start_dir[k]); free(im->pc_start_elecv[k]);
+				free(im->pc_exit_dir[k]); free(im->pc_exit_elecv[k]);
+			}
+			for (int k = 0; k < 3; k++)
+				free(im->pc_exit_coords[k]);
+			free(im->pc_exit_nrefl); free(im->pc_exit_dtravel); free(im->exit_coord_weights);
+		}
 		for (int k = 0; k < 2; k++) {
-			free(im->src_start_coords[k]); free(im->pc_start_coords[k]); free(im->pc_start_dir[k]); free(im->pc_start_elecv[k]);
-			free(im->pc_exit_dir[k]); free(im->pc_exit_elecv[k]); free(im->extleak_dir[k]); free(im->intleak_dir[k]); free(im->intleak_elecv[k]);
+			free(im->extleak_dir[k]); free(im->intleak_dir[k]); free(im->intleak_elecv[k]);
 		}
 		for (int k = 0; k < 3; k++) {
-			free(im->pc_exit_coords[k]); free(im->extleak_coords[k]); free(im->intleak_coords[k]);
+			free(im->extleak_coords[k]); free(im->intleak_coords[k]);
 		}
-		free(im->pc_exit_nrefl); free(im->pc_exit_dtravel); free(im->exit_coord_weights);
 		free(im->extleak_coord_weights); free(im->extleak_n_refl); free(im->intleak_coord_weights); free(im->intleak_n_refl);
 		free(im);
 	}
 	free(eff);
+	if (arena.p)
+		arena_release(arena);
 }
 
 extern "C" bool polycap_transmission_efficiencies_get_data(polycap_transmission_efficiencies *eff, size_t *n_energies, double **energies_arr,

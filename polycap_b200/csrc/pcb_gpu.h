@@ -101,6 +101,8 @@ int pcb_gpu_last_wave_dense(pcb_gpu_optic *g, int64_t n_ids, int8_t *status, dou
 /* device memory helpers for callers that do not link the CUDA runtime */
 void *pcb_gpu_malloc(int device, size_t bytes);
 void pcb_gpu_free(int device, void *p);
+void *pcb_gpu_host_alloc(size_t bytes); /* pinned, portable */
+void pcb_gpu_host_free(void *p);
 int pcb_gpu_memset(int device, void *p, int v, size_t bytes, void *stream);
 int pcb_gpu_copy_to_host(int device, void *dst, const void *src_dev, size_t bytes, void *stream);
 int pcb_gpu_sync(int device, void *stream);

@@ -1017,6 +1017,16 @@ extern "C" void pcb_gpu_free(int device, void *p)
 	cudaSetDevice(pick_device(device));
 	cudaFree(p);
 }
+extern "C" void *pcb_gpu_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+		g_last_error = "cudaHostAlloc failed for the result arrays";
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void pcb_gpu_host_free(void *p) { cudaFreeHost(p); }
 extern "C" int pcb_gpu_memset(int device, void *p, int v, size_t bytes, void *stream)
 {
 	CK(cudaSetDevice(pick_device(device)));
