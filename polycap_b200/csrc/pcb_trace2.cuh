@@ -41,6 +41,9 @@
 #ifndef T2_CONSENSUS
 #define T2_CONSENSUS 1 /* the warps of a CTA prefer the same long task (see the claim code); 0: fullest queue wins every time */
 #endif
+#ifndef T2_PREFETCH
+#define T2_PREFETCH 64 /* energies ahead to prefetch in the dealt energy loop (0: off) */
+#endif
 #ifndef T2_SPREAD_ILP
 #define T2_SPREAD_ILP 2 /* (photon, energy) pairs in flight per lane in the dealt energy loop */
 #endif
@@ -628,6 +631,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 							sl[u] = batch[pu[u]];
 							wp[u] = wcta + (unsigned long long)sl[u] * nE + eu[u];
 							w[u] = *wp[u];
+#if T2_PREFETCH
+							/* the lane's pair of the round after next is 128 energies further in the same weight vector (when the
+							 * vector is that long): pull it towards the L2 now -- at nE = 291 the pool's vectors (397 MB) live in DRAM */
+							if (eu[u] + T2_PREFETCH < nE)
+								asm volatile("prefetch.global.L2 [%0];" ::"l"(wp[u] + T2_PREFETCH));
+#endif
 						}
 #pragma unroll
 						for (int u = 0; u < U; u++)
