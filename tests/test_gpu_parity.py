@@ -322,3 +322,32 @@ def test_shared_divisor_division_is_ieee(pc):
     IEEE `a / b` on the device: ordinary magnitudes, wide exponent ranges, and the full range incl. 0 / subnormal / inf / NaN"""
     for seed, span in ((1, 3), (2, 40), (3, 400), (4, 1000), (5, 1100)):
         assert pc.selftest_division(1 << 25, seed, span) == 0, (seed, span)
+
+
+def test_repeated_calls_are_identical_whatever_the_wave_partition(pc, monkeypatch):
+    """The first call of a source sizes its waves from a probe, later calls from the exit fraction the previous call ended
+    with (one wave); photons are addressed by id, so the results must not depend on that -- nor on whether the exit records
+    land in a pinned or a pageable host block."""
+    monkeypatch.setenv("POLYCAP_B200_SEED", "4242")
+    prof = pc.Profile(pc.Profile.ELLIPSOIDAL, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5)
+    desc = pc.Description(prof, 0.0, 200000, {8: 53.0, 14: 47.0}, 2.23)
+    src = pc.Source(desc, 2000.0, 0.2065, 0.2065, 0.0, 0.0, 0.0, 0.0, 0.5, [3.0, 9.0, 17.5])
+    first = src.get_transmission_efficiencies(-1, 20000, False)
+    second = src.get_transmission_efficiencies(-1, 20000, False)
+    monkeypatch.setenv("POLYCAP_B200_PAGEABLE_RESULTS", "1")
+    third = src.get_transmission_efficiencies(-1, 20000, False)
+    a, b, c = first.records, second.records, third.records
+    assert a["i_start"] == b["i_start"] == c["i_start"]
+    # per-photon records are identical; the tallies are sums over waves, i.e. the same terms in a different grouping
+    assert np.allclose(first.data[1], second.data[1], rtol=1e-13, atol=0) and np.array_equal(second.data[1], third.data[1])
+    for key in ("pc_exit_coords", "pc_exit_dir", "pc_start_coords", "src_start_coords", "pc_exit_elecv"):
+        for x, y, z in zip(a[key], b[key], c[key]):
+            assert np.array_equal(x, y) and np.array_equal(x, z), key
+    assert np.array_equal(a["exit_coord_weights"], b["exit_coord_weights"]) and np.array_equal(a["exit_coord_weights"], c["exit_coord_weights"])
+    assert np.array_equal(a["pc_exit_nrefl"], b["pc_exit_nrefl"]) and np.array_equal(a["pc_exit_nrefl"], c["pc_exit_nrefl"])
+    # results stay valid after the objects that shared their pool blocks are gone
+    keep = a["exit_coord_weights"].copy()
+    del second, third, b, c
+    again = src.get_transmission_efficiencies(-1, 20000, False)
+    assert np.array_equal(a["exit_coord_weights"], keep)
+    assert np.array_equal(again.records["exit_coord_weights"], keep)
