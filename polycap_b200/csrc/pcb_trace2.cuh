@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				const unsigned go = __ballot_sync(0xffffffffu, hitting);
 				const int n_go = __popc(go);
 				if (hitting) {
-					SD(D_G0) = g_ct; SD(D_G1) = g_st; SD(D_LHZ) = g_fs; SD(D_AUX) = alfa;
+					SD(D_G0) = g_ct; SD(D_G1) = EXACT_W ? g_st : g_st * g_st; SD(D_LHZ) = g_fs; SD(D_AUX) = alfa; /* cheap weights: sin^2 */
 					batch[__popc(go & ((1u << lane) - 1u))] = (unsigned short)slot;
 					if (!(flags & F_WINIT)) { /* first reflection: the weight vector starts at 1 */
 						double *w0 = wcta + (unsigned long long)slot * nE;
@@ -640,9 +640,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						}
 #pragma unroll
 						for (int u = 0; u < U; u++)
-							r[u] = fresnel_rtot_fast(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
-										 __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_G0][sl[u]], S.d[D_G1][sl[u]], S.d[D_LHZ][sl[u]],
-										 1. - S.d[D_LHZ][sl[u]]);
+							r[u] = fresnel_rtot_fast_s2(__ldg(ec + EC_NRE * nE + eu[u]), __ldg(ec + EC_NIM * nE + eu[u]), __ldg(ec + EC_I2RE * nE + eu[u]),
+										    __ldg(ec + EC_I2IM * nE + eu[u]), S.d[D_G0][sl[u]], S.d[D_G1][sl[u]], S.d[D_LHZ][sl[u]]);
 #pragma unroll
 						for (int u = 0; u < U; u++) {
 							if (rough) {
@@ -672,7 +671,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						const double i2_re = __ldg(ec + EC_I2RE * nE + e), i2_im = __ldg(ec + EC_I2IM * nE + e);
 						const double c_t = S.d[D_G0][sl], s_t = S.d[D_G1][sl], f_s = S.d[D_LHZ][sl];
 						const double rtot = EXACT_W ? fresnel_rtot(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s)
-									    : fresnel_rtot_fast(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s, 1. - f_s);
+									    : fresnel_rtot_fast_s2(n_re, n_im, i2_re, i2_im, c_t, s_t, f_s); /* s_t holds sin^2 here */
 						if (rough) {
 							const double cons1 = __ldg(ec + EC_KR * nE + e) * S.d[D_AUX][sl] * sig_rough;
 							w = w * rtot * exp(-1. * cons1 * cons1);
