@@ -148,28 +148,56 @@ def reference_run(ref, src, n_exit, threads=-1):
     im = eff.contents.images.contents
     started, exits = im.i_start, im.i_exit
     refl = int(np.ctypeslib.as_array(im.pc_exit_nrefl, (exits,)).sum())
+    nE = eff.contents.n_energies
+    # Sum of exit weights per energy, recovered from the efficiencies the reference returns (source.c:1075: eff = sum_w / started)
+    sum_w = np.ctypeslib.as_array(eff.contents.efficiencies, (nE,)).copy() * started
     ref.L.polycap_transmission_efficiencies_free(eff)
-    return dt, started, exits, refl
+    return dt, started, exits, refl, sum_w
 
 
 def reference_sample(w, seconds, steps=1, warmup=0):
     """bounded sample: n_exit sized from a probe so that one call takes about `seconds`"""
     ref, src = reference_setup(w)
     cores = os.cpu_count() or 1
-    dt, started, exits, _ = reference_run(ref, src, 40)
-    n = max(40, int(40 * seconds / max(dt, 1e-3)))
+    dt, started, exits, _, _ = reference_run(ref, src, 40)  # first call: thread start-up dominates, only good for an order of magnitude
+    n1 = max(40, int(40 * 1.0 / max(dt, 1e-3)))
+    dt, started, exits, _, _ = reference_run(ref, src, n1)  # ~1 s probe
+    n = max(40, int(n1 * seconds / max(dt, 1e-3)))
     for _ in range(warmup):
         reference_run(ref, src, max(40, n // 4))
     tot_t = tot_started = tot_refl = tot_exit = 0
+    tot_w = 0.0
     for _ in range(steps):
-        dt, started, exits, refl = reference_run(ref, src, n)
+        dt, started, exits, refl, sum_w = reference_run(ref, src, n)
         tot_t += dt; tot_started += started; tot_refl += refl; tot_exit += exits
+        tot_w = tot_w + sum_w
     ref.L.polycap_source_free(src)
     return dict(value=tot_started / tot_t, unit="photons/s", cores=cores, kind="reference",
                 sample="%d call(s) of the reference's polycap_source_get_transmission_efficiencies (oracle/_ref: its own sources, gcc -O2 -fopenmp, "
                        "xraylib replaced by the built-in optical-constants table => per-photon scatf is cheaper than with real xraylib), "
                        "n_photons=%d exits/call = %d simulated photons in %.1f s on %d host threads" % (steps, n, tot_started, tot_t, cores),
-                exit_photons_per_s=tot_exit / tot_t, reflections_of_exit_photons_per_s=tot_refl / tot_t, ms_per_step=1e3 * tot_t / steps)
+                exit_photons_per_s=tot_exit / tot_t, reflections_of_exit_photons_per_s=tot_refl / tot_t, ms_per_step=1e3 * tot_t / steps,
+                started=int(tot_started), exits=int(tot_exit), efficiencies=(tot_w / max(tot_started, 1)).tolist())
+
+
+def stat_parity(eff_gpu, n_gpu, eff_ref, n_ref, exit_gpu=None, exit_ref=None):
+    """north_star check 2: transmission efficiency per energy, GPU vs the reference's own CPU run of the same workload, in units of
+    the binomial standard error at the two photon counts (independent random streams: Philox on the GPU, MT19937 in the reference).
+    A photon's weight lies in [0, 1], so p(1-p)/N bounds the variance of the mean weight p."""
+    eg, er = np.asarray(eff_gpu, dtype=np.float64), np.asarray(eff_ref, dtype=np.float64)
+    pooled = (eg * n_gpu + er * n_ref) / max(n_gpu + n_ref, 1)
+    sigma = np.sqrt(np.maximum(pooled * (1.0 - pooled), 1e-12) * (1.0 / max(n_gpu, 1) + 1.0 / max(n_ref, 1)))
+    z = np.abs(eg - er) / sigma
+    out = {"check": "efficiency per energy: |gpu - reference| / binomial sigma at the two photon counts; pass = all < 3",
+           "n_sigma_max": float(z.max()), "n_sigma_rms": float(np.sqrt(np.mean(z * z))), "energies_over_3_sigma": int((z >= 3).sum()),
+           "n_energies": int(z.size), "pass": bool((z < 3).all()), "photons_gpu": int(n_gpu), "photons_reference": int(n_ref),
+           "max_abs_diff": float(np.abs(eg - er).max())}
+    if exit_gpu is not None and exit_ref is not None:
+        pg, pr = exit_gpu / max(n_gpu, 1), exit_ref / max(n_ref, 1)
+        pp = (exit_gpu + exit_ref) / max(n_gpu + n_ref, 1)
+        out["exit_fraction"] = {"gpu": pg, "reference": pr,
+                                "n_sigma": float(abs(pg - pr) / np.sqrt(max(pp * (1 - pp), 1e-12) * (1.0 / max(n_gpu, 1) + 1.0 / max(n_ref, 1))))}
+    return out
 
 
 # ------------------------------------------------------------------ main
@@ -376,6 +404,7 @@ def main():
             try:
                 b = reference_sample(w, args.cpu_seconds)
                 line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["stat_parity"] = stat_parity(line["efficiencies"], photons, b["efficiencies"], b["started"], cnt["exit"], b["exits"])
             except Exception as exc:  # the checker is optional infrastructure; the GPU numbers stand without it
                 line["cpu_baseline"] = {"value": None, "unit": "photons/s", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: %s" % exc}
         sys.stdout.flush()

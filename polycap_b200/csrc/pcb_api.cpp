@@ -52,7 +52,7 @@ struct CachedOptic {
 	pcb_gpu_optic *g = nullptr;
 	uint64_t stamp = 0;
 };
-static CachedOptic g_cache[4];
+static CachedOptic g_cache[24];
 static uint64_t g_stamp = 0;
 
 static uint64_t fnv(uint64_t h, const void *p, size_t n)
@@ -97,8 +97,10 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 	h = fnv(h, energies, nE * 8);
 	h = fnv(h, amu.data(), nE * 8);
 	h = fnv(h, scatf.data(), nE * 8);
-	h = fnv(h, &device, sizeof device);
-	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS", "POLYCAP_B200_KERNEL"}) { /* modes read at optic creation */
+	const int resolved = pcb_gpu_resolve_device(device); /* -1 -> POLYCAP_B200_DEVICE / current device: an optic lives on ONE device */
+	h = fnv(h, &resolved, sizeof resolved);
+	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS", "POLYCAP_B200_KERNEL", "POLYCAP_B200_DEFER_MIN",
+			      "POLYCAP_B200_DEFER_HK"}) { /* modes read at optic creation */
 		const char *v = getenv(k);
 		h = fnv(h, v ? v : "", v ? strlen(v) + 1 : 1);
 	}
@@ -589,6 +591,10 @@ static ResultArena arena_take(size_t bytes)
 	/* POLYCAP_B200_PAGEABLE_RESULTS=1: plain malloc (a one-shot caller with a multi-GB result does not pay for pinning) */
 	const bool pageable = getenv("POLYCAP_B200_PAGEABLE_RESULTS") != NULL;
 	ResultArena a = {pageable ? malloc(bytes) : pcb_gpu_host_alloc(bytes), bytes, !pageable};
+	if (!a.p && !pageable) { /* pinning a multi-GB block can fail where plain memory is still there: slower downloads, same results */
+		a.p = malloc(bytes);
+		a.pinned = false;
+	}
 	return a;
 }
 
@@ -614,6 +620,48 @@ static void arena_release(ResultArena a)
 			free(drop.p);
 	}
 }
+
+/* Devices of a run.  POLYCAP_B200_DEVICES = "all" or a comma-separated list of CUDA ordinals shards the photon ids of
+ * polycap_source_get_transmission_efficiencies over those devices from this one process (the C API has one caller
+ * thread); unset: one device (POLYCAP_B200_DEVICE or the calling thread's current device). */
+static std::vector<int> run_devices()
+{
+	std::vector<int> out;
+	const char *e = getenv("POLYCAP_B200_DEVICES");
+	if (!e || !*e) {
+		out.push_back(-1);
+		return out;
+	}
+	const int n = pcb_gpu_device_count();
+	if (!strcmp(e, "all")) {
+		for (int i = 0; i < n && i < 16; i++)
+			out.push_back(i);
+	} else {
+		const char *p = e;
+		while (*p) {
+			char *end;
+			long v = strtol(p, &end, 10);
+			if (end == p)
+				break;
+			if (v >= 0 && v < n && std::find(out.begin(), out.end(), (int)v) == out.end() && out.size() < 16)
+				out.push_back((int)v);
+			p = (*end == ',') ? end + 1 : end;
+		}
+	}
+	if (out.empty())
+		out.push_back(-1);
+	return out;
+}
+
+struct DevRun { /* one device's share of a run */
+	pcb_gpu_optic *g;
+	int dev;
+	double *d_sum;
+	int64_t *d_cnt;
+	double *d_rf, *d_rw;
+	int64_t rec_cap, rec_used;
+	int64_t n_ids, exits; /* current wave */
+};
 
 extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_efficiencies(polycap_source *source, int max_threads, int n_photons,
 											    bool leak_calc, polycap_progress_monitor *progress_monitor,

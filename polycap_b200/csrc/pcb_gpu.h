@@ -45,6 +45,8 @@ enum {
 
 const char *pcb_gpu_last_error(void);
 int pcb_gpu_device_count(void);
+/* the device a request for `device` lands on (-1: env POLYCAP_B200_DEVICE, else the calling thread's current device) */
+int pcb_gpu_resolve_device(int device);
 
 /* Uploads profile tables and per-energy optical constants to `device` (-1: current default). */
 pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc *d);
@@ -82,6 +84,25 @@ int pcb_gpu_replay(pcb_gpu_optic *g, int64_t n, const double *coords, const doub
 int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted,
 		     double *d_sum_weights, int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap, int64_t rec_base,
 		     void *stream, int64_t *ids_used, int64_t *n_exit);
+
+/* The same wave in two asynchronous phases on the optic's own stream, so that a run over several devices can place the cut
+ * between them and record downloads overlap the next trace (pcb_api.cpp: polycap_source_get_transmission_efficiencies).
+ *   begin     trace ids [id0, id0+n_ids) and rank the exit photons          wave_count     wait; exits of the whole wave
+ *   finish    cut after the n_wanted-th exit (0: none), tally, compact      wave_result    wait; ids / exits below the cut
+ *   download  records -> host arrays [17][host_cap], [host_cap][nE] on the copy stream, after that wave's finish
+ *   reuse_records  the next finish may overwrite the record buffer from its start (waits for the downloads queued so far) */
+void *pcb_gpu_optic_stream(pcb_gpu_optic *g);
+int pcb_gpu_wave_begin(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids);
+int pcb_gpu_wave_count(pcb_gpu_optic *g, int64_t *exits);
+int pcb_gpu_wave_finish(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *d_sum_weights, int64_t *d_counters, double *d_rec_fields,
+			double *d_rec_weights, int64_t rec_cap, int64_t rec_base);
+int pcb_gpu_wave_result(pcb_gpu_optic *g, int64_t *ids_used, int64_t *n_exit);
+int pcb_gpu_wave_download(pcb_gpu_optic *g, const double *d_rec_fields, const double *d_rec_weights, int64_t rec_cap, int64_t rec_base, int64_t n,
+			  double *h_fields, double *h_weights, int64_t host_cap, int64_t host_base);
+int pcb_gpu_wave_reuse_records(pcb_gpu_optic *g);
+int pcb_gpu_wave_download_sync(pcb_gpu_optic *g);
+/* sum over n devices of their tallies -> host (peer reads over NVLink when available, else staged; fixed device order) */
+int pcb_gpu_reduce_tallies(pcb_gpu_optic *const *optics, double *const *d_sum, int64_t *const *d_cnt, int n, double *h_sum, int64_t *h_cnt, int *used_peer);
 
 /* start state the tracer draws for ids [id0, id0+n): out[n][11] = coords(3) dir(3) elecv(3) src_x src_y (host memory) */
 int pcb_gpu_sample_ids(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n, double *out_host);

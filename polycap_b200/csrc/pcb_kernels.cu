@@ -63,6 +63,9 @@ struct pcb_gpu_optic {
 	double *d_tables = nullptr; /* z, cap, ext, hexz, rm: 5 x tb bytes */
 	double *d_ec = nullptr;
 	double *d_wscratch = nullptr;
+	double *d_hist = nullptr; /* deferred weights: reflection history of the pool slots */
+	int defer_min = 48;	  /* deferred weights for grids of at least this many energies (source-driven runs, cheap weights) */
+	int hk = 0;		  /* history entries per flush (0: from the energy count) */
 	PcbWorkCounters *d_wc = nullptr;
 	size_t table_bytes = 0; /* tb */
 	int threads = PCB_LB_THREADS, ctas_per_sm = PCB_LB_CTAS;
@@ -97,6 +100,11 @@ struct pcb_gpu_optic {
 	/* replay buffers */
 	int64_t replay_cap = 0;
 	double *d_rin = nullptr;
+	/* two-phase waves (multi-device runs, pipelined record download): the optic's own streams and a pinned word block the
+	 * device copies wave counts into ([0] ids below the cut, [1] exits below the cut, [2] exits of the whole wave) */
+	cudaStream_t s_main = nullptr, s_copy = nullptr;
+	cudaEvent_t ev_fin = nullptr, ev_copy = nullptr;
+	int64_t *h_pin = nullptr;
 	/* instrumentation: kernels launched, and (when timing is on) CUDA-event pairs around every trace kernel */
 	int64_t n_kernels = 0, n_trace = 0;
 	int timing = 0;
@@ -119,6 +127,8 @@ static int pick_device(int device)
 	return cur;
 }
 
+extern "C" int pcb_gpu_resolve_device(int device) { return pick_device(device); }
+
 extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc *d)
 {
 	int ndev = pcb_gpu_device_count();
@@ -138,8 +148,8 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 		g_last_error = "cudaGetDeviceProperties failed";
 		return nullptr;
 	}
-	if (prop.major < 9) {
-		g_last_error = "polycap-b200 needs an sm_100a (Blackwell) device";
+	if (prop.major != 10 || prop.minor != 0) { /* the library carries sm_100a code only (no PTX) */
+		g_last_error = "polycap-b200 needs an sm_100a (Blackwell B200) device";
 		return nullptr;
 	}
 	pcb_gpu_optic *g = new pcb_gpu_optic();
@@ -243,6 +253,8 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 	if ((e = getenv("POLYCAP_B200_CTAS_PER_SM"))) g->ctas_per_sm = atoi(e);
 	if ((e = getenv("POLYCAP_B200_EXACT_FRESNEL"))) g->exact_weights = atoi(e);
 	if ((e = getenv("POLYCAP_B200_KERNEL"))) g->kernel_version = atoi(e);
+	if ((e = getenv("POLYCAP_B200_DEFER_MIN"))) g->defer_min = atoi(e); /* 0: never defer */
+	if ((e = getenv("POLYCAP_B200_DEFER_HK"))) g->hk = atoi(e);
 	if (t2_smem_bytes((int)tn) > 227 * 1024)
 		g->kernel_version = 1; /* profile too long for the shared-memory pool */
 	return g;
@@ -253,13 +265,18 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	if (!g)
 		return;
 	cudaSetDevice(g->device);
-	cudaFree(g->d_tables); cudaFree(g->d_ec); cudaFree(g->d_wscratch); cudaFree(g->d_wc);
+	cudaFree(g->d_tables); cudaFree(g->d_ec); cudaFree(g->d_wscratch); cudaFree(g->d_hist); cudaFree(g->d_wc);
 	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights);
 	cudaFree(g->d_rank); cudaFree(g->d_blocksum); cudaFree(g->d_cutinfo); cudaFree(g->d_partial); cudaFree(g->d_cpartial);
 	cudaFree(g->d_rin);
 	cudaFreeHost(g->h_tables);
 	cudaFreeHost(g->h_ec);
 	cudaFreeHost(g->h_stage);
+	cudaFreeHost(g->h_pin);
+	if (g->s_main) cudaStreamDestroy(g->s_main);
+	if (g->s_copy) cudaStreamDestroy(g->s_copy);
+	if (g->ev_fin) cudaEventDestroy(g->ev_fin);
+	if (g->ev_copy) cudaEventDestroy(g->ev_copy);
 	cudaFree(g->d_result);
 	for (auto &p : g->ev_pending) {
 		cudaEventDestroy(p.first);
@@ -393,6 +410,14 @@ extern "C" void pcb_gpu_optic_tune(pcb_gpu_optic *g, int thr_cand, int thr_refl,
 
 static const int TALLY_BLOCKS = 512;
 
+/* deferred weights (pcb_trace2.cuh, task ENERGY): source-driven runs of the task-queue tracer with the cheap Fresnel term and a
+ * long energy grid.  Replay (polycap_photon_launch) always updates weights reflection by reflection: it returns the state of
+ * absorbed photons too. */
+static bool defer_on(const pcb_gpu_optic *g)
+{
+	return g->kernel_version == 2 && !g->exact_weights && g->defer_min > 0 && g->nE >= g->defer_min;
+}
+
 static int ensure_wave(pcb_gpu_optic *g, int64_t n)
 {
 	if (!g->d_wscratch) {
@@ -401,6 +426,8 @@ static int ensure_wave(pcb_gpu_optic *g, int64_t n)
 			slots = (size_t)g->sm_count * T2_NP;
 		CK(cudaMalloc(&g->d_wscratch, slots * (size_t)g->nE * 8));
 	}
+	if (!g->d_hist && defer_on(g))
+		CK(cudaMalloc(&g->d_hist, (size_t)g->sm_count * T2_NP * T2_HK * 4 * 8));
 	if (n <= g->wave_cap)
 		return 0;
 	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights); cudaFree(g->d_rank);
@@ -435,6 +462,8 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 	P.out.status = g->d_status; P.out.fields = g->d_fields; P.out.irefl = g->d_irefl; P.out.weights = g->d_weights;
 	P.wc = g->d_wc;
 	P.wscratch = g->d_wscratch;
+	P.hist = g->d_hist;
+	P.hk = g->hk > 0 ? (g->hk < T2_HK ? g->hk : T2_HK) : (g->nE >= 128 ? T2_HK : 32);
 	P.id0 = (unsigned long long)id0;
 	P.n_ids = (unsigned long long)n;
 	P.mode = mode;
@@ -459,10 +488,10 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 	g->n_kernels++;
 	g->n_trace++;
 	/* EXACT_W = 1: per-energy Fresnel term in the reference's operation order (bit-level weights); 0: the cheap evaluation */
-#define PCB_LAUNCH(K, M, X)                                                                                     \
+#define PCB_LAUNCH(K, ...)                                                                                      \
 	do {                                                                                                    \
-		CK(cudaFuncSetAttribute(K<M, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-		K<M, X><<<blocks, nthreads, smem, stream>>>(P);                                                 \
+		CK(cudaFuncSetAttribute(K<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		K<__VA_ARGS__><<<blocks, nthreads, smem, stream>>>(P);                                          \
 	} while (0)
 	int nthreads = g->threads;
 	if (g->kernel_version == 2) {
@@ -473,9 +502,11 @@ static int launch_trace(pcb_gpu_optic *g, int mode, const pcb_source_desc *s, ui
 		if (need2 < blocks)
 			blocks = (int)(need2 > 0 ? need2 : 1);
 		if (mode == MODE_SOURCE) {
-			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 1); else PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 0);
+			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 1, 0);
+			else if (defer_on(g) && g->d_hist) PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 0, 1);
+			else PCB_LAUNCH(pcb_trace2_kernel, MODE_SOURCE, 0, 0);
 		} else {
-			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 1); else PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 0);
+			if (g->exact_weights) PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 1, 0); else PCB_LAUNCH(pcb_trace2_kernel, MODE_REPLAY, 0, 0);
 		}
 	} else if (mode == MODE_SOURCE) {
 		if (g->exact_weights) PCB_LAUNCH(pcb_trace_kernel, MODE_SOURCE, 1); else PCB_LAUNCH(pcb_trace_kernel, MODE_SOURCE, 0);
@@ -802,9 +833,10 @@ __global__ void wave_compact_weights(const int8_t *status, const int64_t *rank, 
 	}
 }
 
-/* id-ordered post-processing of the dense per-id outputs in g->d_status/d_irefl/d_fields/d_weights (see file header) */
-static int wave_post(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *d_sum_weights, int64_t *d_counters, double *d_rec_fields,
-		     double *d_rec_weights, int64_t rec_cap, int64_t rec_base, cudaStream_t stream, int64_t *ids_used, int64_t *n_exit)
+/* id-ordered post-processing of the dense per-id outputs in g->d_status/d_irefl/d_fields/d_weights (see file header), in two
+ * steps so that a run over several devices can place the cut between them: wave_scan counts the wave's exit photons
+ * (cutinfo[2]) and ranks them; wave_finish cuts after the n_wanted-th of them, tallies and compacts what lies below the cut. */
+static int wave_scan(pcb_gpu_optic *g, int64_t n_ids, cudaStream_t stream)
 {
 	g->last_wave_n = n_ids;
 	const int nb = (int)((n_ids + SCAN_T - 1) / SCAN_T);
@@ -814,6 +846,15 @@ static int wave_post(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *
 	}
 	wave_scan_blocks<<<nb, SCAN_T, 0, stream>>>(g->d_status, n_ids, g->d_rank, g->d_blocksum);
 	wave_scan_sums<<<1, 1024, 0, stream>>>(g->d_blocksum, nb, g->d_cutinfo);
+	g->n_kernels += 2;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int wave_finish(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *d_sum_weights, int64_t *d_counters, double *d_rec_fields,
+		       double *d_rec_weights, int64_t rec_cap, int64_t rec_base, cudaStream_t stream, int64_t *ids_used, int64_t *n_exit)
+{
+	const int nb = (int)((n_ids + SCAN_T - 1) / SCAN_T);
 	wave_scan_finish<<<nb, SCAN_T, 0, stream>>>(g->d_status, n_ids, g->d_rank, g->d_blocksum, n_wanted, g->d_cutinfo);
 	wave_cut_resolve<<<1, 1, 0, stream>>>(n_ids, n_wanted, g->d_cutinfo);
 	int tb = TALLY_BLOCKS;
@@ -822,7 +863,7 @@ static int wave_post(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *
 	wave_tally_partial<<<tb, 256, 256 * 8, stream>>>(g->d_status, g->d_irefl, g->d_weights, g->nE, n_ids, g->d_cutinfo, g->d_partial, g->d_cpartial);
 	int ft = g->nE > 16 ? g->nE : 16;
 	wave_tally_final<<<(ft + 255) / 256, 256, 0, stream>>>(g->d_partial, g->d_cpartial, tb, g->nE, g->d_cutinfo, g->d_wc, d_sum_weights, d_counters);
-	g->n_kernels += 6;
+	g->n_kernels += 4;
 	if (d_rec_fields && d_rec_weights) {
 		g->n_kernels += 2;
 		wave_compact_fields<<<(unsigned)((n_ids + 255) / 256), 256, 0, stream>>>(g->d_status, g->d_rank, g->d_fields, n_ids, g->d_cutinfo, d_rec_fields,
@@ -854,9 +895,219 @@ extern "C" int pcb_gpu_run_wave(pcb_gpu_optic *g, const pcb_source_desc *s, uint
 	if (ensure_wave(g, n_ids))
 		return -1;
 	PcbReplayIn rin{};
-	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, stream))
+	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, stream) || wave_scan(g, n_ids, stream))
 		return -1;
-	return wave_post(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, ids_used, n_exit);
+	return wave_finish(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, ids_used, n_exit);
+}
+
+/* ---- the same wave in two asynchronous phases on the optic's own stream (pcb_api.cpp drives one optic per device) ---- */
+static int ensure_streams(pcb_gpu_optic *g)
+{
+	if (g->s_main)
+		return 0;
+	/* blocking streams: they keep the implicit ordering with the legacy default stream, which the single-wave entry points
+	 * (replay, run_ids, table re-upload) use; main and copy stream do not order against each other */
+	CK(cudaStreamCreate(&g->s_main));
+	CK(cudaStreamCreate(&g->s_copy));
+	CK(cudaEventCreateWithFlags(&g->ev_fin, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming));
+	CK(cudaHostAlloc((void **)&g->h_pin, 8 * sizeof(int64_t), cudaHostAllocPortable));
+	return 0;
+}
+
+extern "C" void *pcb_gpu_optic_stream(pcb_gpu_optic *g)
+{
+	if (cudaSetDevice(g->device) != cudaSuccess || ensure_streams(g))
+		return nullptr;
+	return (void *)g->s_main;
+}
+
+/* phase 1: trace ids [id0, id0+n_ids), rank the exit photons; their number travels to pinned memory (pcb_gpu_wave_count) */
+extern "C" int pcb_gpu_wave_begin(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids)
+{
+	if (n_ids <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	if (ensure_streams(g) || ensure_wave(g, n_ids))
+		return -1;
+	PcbReplayIn rin{};
+	if (launch_trace(g, MODE_SOURCE, s, seed, id0, n_ids, rin, g->s_main) || wave_scan(g, n_ids, g->s_main))
+		return -1;
+	CK(cudaMemcpyAsync(g->h_pin + 2, g->d_cutinfo + 2, 8, cudaMemcpyDeviceToHost, g->s_main));
+	return 0;
+}
+
+/* waits for phase 1: exit photons of the whole wave */
+extern "C" int pcb_gpu_wave_count(pcb_gpu_optic *g, int64_t *exits)
+{
+	CK(cudaSetDevice(g->device));
+	CK(cudaStreamSynchronize(g->s_main));
+	*exits = g->h_pin[2];
+	return 0;
+}
+
+/* phase 2 (asynchronous): cut after the n_wanted-th exit (0: none), tallies into d_sum_weights / d_counters, records appended at
+ * rec_base of the device record buffer.  pcb_gpu_wave_result waits and returns ids below the cut / exits below the cut. */
+extern "C" int pcb_gpu_wave_finish(pcb_gpu_optic *g, int64_t n_ids, int64_t n_wanted, double *d_sum_weights, int64_t *d_counters, double *d_rec_fields,
+				   double *d_rec_weights, int64_t rec_cap, int64_t rec_base)
+{
+	CK(cudaSetDevice(g->device));
+	if (wave_finish(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, g->s_main, nullptr, nullptr))
+		return -1;
+	CK(cudaMemcpyAsync(g->h_pin, g->d_cutinfo, 16, cudaMemcpyDeviceToHost, g->s_main));
+	CK(cudaEventRecord(g->ev_fin, g->s_main));
+	return 0;
+}
+
+extern "C" int pcb_gpu_wave_result(pcb_gpu_optic *g, int64_t *ids_used, int64_t *n_exit)
+{
+	CK(cudaSetDevice(g->device));
+	CK(cudaStreamSynchronize(g->s_main));
+	*ids_used = g->h_pin[0];
+	*n_exit = g->h_pin[1];
+	return 0;
+}
+
+/* records [rec_base, rec_base + n) of the device record buffer -> host arrays laid out [17][host_cap] / [host_cap][nE], at record
+ * host_base, on the optic's copy stream once phase 2 of the wave that produced them has finished (it overlaps the next trace) */
+extern "C" int pcb_gpu_wave_download(pcb_gpu_optic *g, const double *d_rec_fields, const double *d_rec_weights, int64_t rec_cap, int64_t rec_base, int64_t n,
+				     double *h_fields, double *h_weights, int64_t host_cap, int64_t host_base)
+{
+	if (n <= 0)
+		return 0;
+	CK(cudaSetDevice(g->device));
+	CK(cudaStreamWaitEvent(g->s_copy, g->ev_fin, 0));
+	CK(cudaMemcpy2DAsync(h_fields + host_base, (size_t)host_cap * 8, d_rec_fields + rec_base, (size_t)rec_cap * 8, (size_t)n * 8, 17, cudaMemcpyDeviceToHost,
+			     g->s_copy));
+	CK(cudaMemcpyAsync(h_weights + (size_t)host_base * g->nE, d_rec_weights + (size_t)rec_base * g->nE, (size_t)n * g->nE * 8, cudaMemcpyDeviceToHost,
+			   g->s_copy));
+	CK(cudaEventRecord(g->ev_copy, g->s_copy));
+	return 0;
+}
+
+/* the next phase 2 may overwrite the record buffer from its start: make the main stream wait for the downloads queued so far */
+extern "C" int pcb_gpu_wave_reuse_records(pcb_gpu_optic *g)
+{
+	CK(cudaSetDevice(g->device));
+	CK(cudaStreamWaitEvent(g->s_main, g->ev_copy, 0));
+	return 0;
+}
+
+extern "C" int pcb_gpu_wave_download_sync(pcb_gpu_optic *g)
+{
+	CK(cudaSetDevice(g->device));
+	if (g->s_copy)
+		CK(cudaStreamSynchronize(g->s_copy));
+	return 0;
+}
+
+/* ---- tallies of several devices combined on one of them over peer memory (NVLink): out[i] = sum over devices, fixed order ---- */
+struct PcbPeerPtrs {
+	const double *sum[16];
+	const int64_t *cnt[16];
+	int n;
+};
+__global__ void tally_reduce_peers(PcbPeerPtrs pp, int nE, double *out_sum, int64_t *out_cnt)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < nE) {
+		double acc = 0;
+		for (int d = 0; d < pp.n; d++)
+			acc += pp.sum[d][t];
+		out_sum[t] = acc;
+	}
+	if (t < PCB_C_COUNT) {
+		int64_t acc = 0;
+		for (int d = 0; d < pp.n; d++)
+			acc += pp.cnt[d][t];
+		out_cnt[t] = acc;
+	}
+}
+
+/* Sum of the per-device tallies (device pointers d_sum[k], d_cnt[k] on the devices of optics[k]) -> host.  With peer access the
+ * first device reads the others' buffers directly (one kernel, one download); without it the buffers are staged through the host.
+ * Either way the terms are added in device order, so the result does not depend on the path.  *used_peer reports which. */
+extern "C" int pcb_gpu_reduce_tallies(pcb_gpu_optic *const *optics, double *const *d_sum, int64_t *const *d_cnt, int n, double *h_sum, int64_t *h_cnt,
+				      int *used_peer)
+{
+	if (n < 1 || n > 16) {
+		g_last_error = "pcb_gpu_reduce_tallies: 1..16 devices";
+		return -1;
+	}
+	pcb_gpu_optic *g0 = optics[0];
+	const int nE = g0->nE;
+	bool peer = n > 1 && !getenv("POLYCAP_B200_NO_PEER");
+	for (int k = 1; k < n && peer; k++) {
+		int can = 0;
+		if (optics[k]->device == g0->device)
+			continue;
+		if (cudaDeviceCanAccessPeer(&can, g0->device, optics[k]->device) != cudaSuccess || !can)
+			peer = false;
+	}
+	if (used_peer)
+		*used_peer = peer ? 1 : 0;
+	for (int k = 0; k < n; k++) { /* every device's waves are complete */
+		CK(cudaSetDevice(optics[k]->device));
+		if (optics[k]->s_main)
+			CK(cudaStreamSynchronize(optics[k]->s_main));
+	}
+	CK(cudaSetDevice(g0->device));
+	if (n == 1) {
+		CK(cudaMemcpy(h_sum, d_sum[0], (size_t)nE * 8, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(h_cnt, d_cnt[0], PCB_C_COUNT * 8, cudaMemcpyDeviceToHost));
+		return 0;
+	}
+	if (peer) {
+		for (int k = 1; k < n; k++)
+			if (optics[k]->device != g0->device) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(optics[k]->device, 0);
+				if (e == cudaErrorPeerAccessAlreadyEnabled)
+					cudaGetLastError();
+				else if (e != cudaSuccess) {
+					cudaGetLastError();
+					peer = false;
+					if (used_peer)
+						*used_peer = 0;
+					break;
+				}
+			}
+	}
+	if (peer) {
+		PcbPeerPtrs pp{};
+		pp.n = n;
+		for (int k = 0; k < n; k++) {
+			pp.sum[k] = d_sum[k];
+			pp.cnt[k] = d_cnt[k];
+		}
+		double *out = nullptr;
+		CK(cudaMalloc(&out, (size_t)nE * 8 + PCB_C_COUNT * 8));
+		int64_t *out_c = (int64_t *)(out + nE);
+		const int nt = nE > PCB_C_COUNT ? nE : PCB_C_COUNT;
+		tally_reduce_peers<<<(nt + 255) / 256, 256>>>(pp, nE, out, out_c);
+		g0->n_kernels++;
+		cudaError_t e1 = cudaMemcpy(h_sum, out, (size_t)nE * 8, cudaMemcpyDeviceToHost);
+		cudaError_t e2 = cudaMemcpy(h_cnt, out_c, PCB_C_COUNT * 8, cudaMemcpyDeviceToHost);
+		cudaFree(out);
+		CK(e1);
+		CK(e2);
+		return 0;
+	}
+	std::vector<double> ts((size_t)nE);
+	int64_t tc[PCB_C_COUNT];
+	for (int i = 0; i < nE; i++)
+		h_sum[i] = 0;
+	for (int i = 0; i < PCB_C_COUNT; i++)
+		h_cnt[i] = 0;
+	for (int k = 0; k < n; k++) {
+		CK(cudaSetDevice(optics[k]->device));
+		CK(cudaMemcpy(ts.data(), d_sum[k], (size_t)nE * 8, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(tc, d_cnt[k], sizeof tc, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < nE; i++)
+			h_sum[i] += ts[i];
+		for (int i = 0; i < PCB_C_COUNT; i++)
+			h_cnt[i] += tc[i];
+	}
+	return 0;
 }
 
 /* ------------------------------------------------------------------ leak_calc = true (pcb_leak.cu) */
@@ -949,7 +1200,8 @@ extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s,
 		return -1;
 	}
 	int64_t used = 0, got = 0;
-	if (wave_post(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, &used, &got)) {
+	if (wave_scan(g, n_ids, stream) ||
+	    wave_finish(g, n_ids, n_wanted, d_sum_weights, d_counters, d_rec_fields, d_rec_weights, rec_cap, rec_base, stream, &used, &got)) {
 		free(recs);
 		return -1;
 	}

@@ -61,6 +61,8 @@ struct PcbTraceParams {
 	PcbWaveOut out;
 	PcbWorkCounters *wc;
 	double *wscratch;          /* [total_threads][nE]: one weight vector per persistent lane */
+	double *hist;              /* task-queue tracer, deferred weights: [CTA][slot][T2_HK][4] reflection history (NULL otherwise) */
+	int hk;                    /* ... entries after which a slot's history is evaluated (<= T2_HK) */
 	unsigned long long id0;    /* global id of local index 0 */
 	unsigned long long n_ids;
 	int mode;

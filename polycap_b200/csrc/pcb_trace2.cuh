@@ -47,12 +47,23 @@
 #ifndef T2_SPREAD_ILP
 #define T2_SPREAD_ILP 2 /* (photon, energy) pairs in flight per lane in the dealt energy loop */
 #endif
+#ifndef T2_HK
+#define T2_HK 64 /* deferred weights: reflection-history entries per slot (the history is flushed at P.hk <= T2_HK entries) */
+#endif
+#ifndef T2_EU
+#define T2_EU 2 /* deferred weights: energies per lane and pass in the energy task (independent FP64 chains per lane) */
+#endif
+#ifndef T2_BACKOFF_MAX
+#define T2_BACKOFF_MAX 4096u /* longest sleep of a warp that finds every queue empty [ns] */
+#endif
 #define T2_EMPTY 0xFFFFu
 
-enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_REFL, TQ_DONE, TQ_N };
+enum { TQ_NEW = 0, TQ_SCAN, TQ_HIT, TQ_REFL, TQ_DONE, TQ_ENERGY, TQ_N };
 
-/* flag bits of a photon slot */
-enum { F_SLOW = 1, F_DEEP = 2, F_WINIT = 4, F_INCUR = 8, F_INNXT = 16 };
+/* flag bits of a photon slot.  F_WINIT: the slot's weight vector in the scratch is valid.  Deferred weights only: F_FAILHIT = the
+ * photon's last wall hit was rejected after it had been accepted as a reflection event (counted when the history is evaluated),
+ * F_WOUT = the final weight vector has been written to the wave output */
+enum { F_SLOW = 1, F_DEEP = 2, F_WINIT = 4, F_INCUR = 8, F_INNXT = 16, F_FAILHIT = 32, F_WOUT = 64 };
 
 struct T2Dbl { /* the 16 double fields of the pool: ex ey ez dx dy dz vx vy vz g0 g1 lhz dtrav A B aux (g0, g1, lhz, aux double as the staging of the reflection geometry), each [T2_NP] */
 	double *base;
@@ -64,6 +75,8 @@ struct T2Shared { /* pointers into dynamic shared memory */
 	int *irefl, *ix, *iseg, *ntrace;
 	unsigned char *flags;
 	signed char *code;
+	unsigned char *nh;   /* deferred weights: buffered reflections of the slot */
+	signed char *resume; /* deferred weights: queue the photon continues in after its history has been evaluated */
 	volatile unsigned short *qbase; /* TQ_N rings of T2_QCAP entries, back to back */
 	__device__ __forceinline__ volatile unsigned short *q(int k) const { return qbase + k * T2_QCAP; }
 };
@@ -79,7 +92,7 @@ __device__ __forceinline__ void t2_push(volatile unsigned short *buf, unsigned *
 	buf[t] = (unsigned short)slot;
 }
 
-template <int MODE, int EXACT_W>
+template <int MODE, int EXACT_W, int DEFER>
 __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTraceParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,7 +133,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 	p += (T2_THREADS / 32) * 32 * 2;
 	S.flags = p; p += T2_NP;
 	S.code = reinterpret_cast<signed char *>(p); p += T2_NP;
-	p += (16 - (2 * T2_NP) % 16) % 16;
+	S.nh = p; p += T2_NP;
+	S.resume = reinterpret_cast<signed char *>(p); p += T2_NP;
+	p += (16 - (4 * T2_NP) % 16) % 16;
 	unsigned *wstat = reinterpret_cast<unsigned *>(p);
 	p += (T2_THREADS / 32) * 16 * 4;
 
@@ -161,6 +176,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 
 	const double *ec = o.ec;
 	double *wcta = P.wscratch + (unsigned long long)blockIdx.x * T2_NP * (unsigned long long)nE; /* weight vector of slot s at wcta + s*nE */
+	/* deferred weights: reflection history of slot s, T2_HK entries of 4 doubles (cos theta, sin^2 theta, frac_s, cos alfa) */
+	double *hcta = DEFER ? P.hist + (unsigned long long)blockIdx.x * T2_NP * (unsigned long long)(T2_HK * 4) : nullptr;
 	/* work and scheduler counters live in shared memory, one row per warp, updated by lane 0 (they would cost 12 registers) */
 	enum { W_STEPS = 0, W_SOLVES, W_REFL, W_LAUNCH, W_BATCHES, W_LANES, W_EMPTY, W_LOST, W_HIT_B, W_HIT_L, W_SCAN_B, W_SCAN_L, W_N = 16 };
 	volatile unsigned *wst = wstat + warp * W_N;
@@ -358,15 +375,22 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				else if (T2_CONSENSUS && (full & (1u << c)))
 					type = c;
 				else {
-					const unsigned key = __reduce_max_sync(0xffffffffu, lane < TQ_N ? ((cnt << 3) | (unsigned)lane) : 0u);
-					type = (int)(key & 7u);
-					if (lane == 0 && type != c && (type == TQ_HIT || type == TQ_REFL))
-						*vcur = type;
+					/* deferred weights: an entry of the energy queue is a whole photon's worth of full-lane work whatever the
+					 * batch size, so it is taken before any PARTIAL batch of the per-photon tasks (and after their full ones) */
+					const unsigned key = __reduce_max_sync(0xffffffffu, (lane < TQ_N && !(DEFER && lane == TQ_ENERGY)) ? ((cnt << 3) | (unsigned)lane) : 0u);
+					if (DEFER && (any & (1u << TQ_ENERGY)) && (key >> 3) < 32u) {
+						type = TQ_ENERGY;
+					} else {
+						type = (int)(key & 7u);
+						if (lane == 0 && type != c && (type == TQ_HIT || type == TQ_REFL))
+							*vcur = type;
+					}
 				}
 				if (lane == 0) {
 					const unsigned h = vhead[type];
 					const unsigned avail = vtail[type] - h;
-					const unsigned want = avail < 32u ? avail : 32u;
+					const unsigned lim = (DEFER && type == TQ_ENERGY) ? 1u : 32u;
+					const unsigned want = avail < lim ? avail : lim;
 					if (want == 0 || atomicCAS(&q_head[type], h, h + want) != h)
 						n = 0;
 					else {
@@ -387,7 +411,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				if (lane == 0)
 					wst[W_EMPTY]++;
 				__nanosleep(backoff); /* all photons are in other warps' hands: back off so the pollers leave the issue slots alone */
-				if (backoff < 4096u)
+				if (backoff < T2_BACKOFF_MAX)
 					backoff <<= 1;
 				continue;
 			}
@@ -488,7 +512,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 							snx = sn.x; sny = sn.y; snz = sn.z;
 							cosalfa = ca;
 							hitting = true;
-							t_steps += 1u << 16;
+							if (!DEFER)
+								t_steps += 1u << 16; /* deferred weights: reflection events are counted when the history is evaluated */
 							const double rx = hit.x - ex, ry = hit.y - ey, rz = hit.z - ez;
 							SD(D_DTRAV) = SD(D_DTRAV) + sqrt(rx * rx + ry * ry + rz * rz); /* capil.c:1315-1319 */
 							ex = hit.x; ey = hit.y; ez = hit.z;
@@ -497,6 +522,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 								code = -1;
 								next = TQ_DONE;
 								hitting = false;
+								flags |= F_FAILHIT;
 							}
 						}
 					} else {
@@ -534,6 +560,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 							code = -1;
 							next = TQ_DONE;
 							hitting = false;
+							flags |= F_FAILHIT;
 						}
 					}
 				}
@@ -575,6 +602,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						code = -1;
 						next = TQ_DONE;
 						hitting = false;
+						flags |= F_FAILHIT;
 					} else {
 						V3 ev = {SD(D_VX), SD(D_VY), SD(D_VZ)};
 						ReflGeom g;
@@ -591,7 +619,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 			const bool rough = (o.sig_rough != 0.0);
 			const double sig_rough = o.sig_rough;
 			bool w_alive = false, w_bad = false;
-			{
+			bool flush = false;
+			if (DEFER) {
+				/* deferred weights: the reflection's energy-independent terms join the slot's history; the per-energy products are
+				 * evaluated by the energy task for the whole history at once, weights in registers.  The photon is traced on as
+				 * alive; a photon that the evaluation finds absorbed earlier is rolled back there (only its classification,
+				 * reflection count and weights are ever read). */
+				if (hitting) {
+					int nh = S.nh[slot];
+					double2 *hp = reinterpret_cast<double2 *>(hcta + ((unsigned long long)slot * T2_HK + nh) * 4);
+					hp[0] = make_double2(g_ct, g_st * g_st);
+					hp[1] = make_double2(g_fs, alfa);
+					nh++;
+					S.nh[slot] = (unsigned char)nh;
+					w_alive = true;
+					flush = nh >= P.hk;
+				}
+			} else {
 				/* the batch's (photon, energy) pairs are dealt over all lanes, whatever the photons' energy count.  The geometry of each
 				 * reflecting photon is staged in its slot (fields that are rewritten before they are read again), readable by every
 				 * lane.  (A loop in which every lane walks its own photon's energies measured 5 % slower even for 10 energies.) */
@@ -698,7 +742,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				w_bad = (bad_bits >> rank) & 1u;
 			}
 			if (hitting) {
-				flags |= F_WINIT;
+				if (!DEFER)
+					flags |= F_WINIT;
 				if (w_bad) {
 					code = -1;
 					next = TQ_DONE;
@@ -722,6 +767,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				} else {
 					code = 0;
 					next = TQ_DONE;
+				}
+				if (DEFER && flush && next != TQ_DONE) { /* history full: evaluate it, then carry on where the photon was headed */
+					S.resume[slot] = (signed char)next;
+					next = TQ_ENERGY;
 				}
 			}
 			if (act) {
@@ -791,12 +840,131 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					F[15 * nn + lid] = (double)irefl;
 					F[16 * nn + lid] = dtrav + sqrt((px - ex) * (px - ex) + (py - ey) * (py - ey) + (zt - ez) * (zt - ez));
 				}
-				if (wr_rec || status == ST_ABSORBED) {
+				if (DEFER) {
+					if (flags & F_FAILHIT)
+						t_steps += 1u << 16; /* a rejected last wall hit that the evaluation of the history did not roll back */
+					if ((wr_rec || status == ST_ABSORBED) && !(flags & F_WOUT)) { /* no reflection since the last evaluation (if any): the scratch holds the weights */
+						double *W = P.out.weights + (unsigned long long)lid * nE;
+						_Pragma("unroll 2") for (int e2 = 0; e2 < nE; e2++)
+							W[e2] = w_init ? wsl[e2] : 1.0;
+					}
+				} else if (wr_rec || status == ST_ABSORBED) {
 					double *W = P.out.weights + (unsigned long long)lid * nE;
 					_Pragma("unroll 2") for (int e2 = 0; e2 < nE; e2++)
 						W[e2] = w_init ? wsl[e2] : 1.0;
 				}
 				next = TQ_NEW;
+			}
+		} else if (DEFER && type == TQ_ENERGY) {
+			/* ---------------- ENERGY (deferred weights): capil_reflect's energy loop (capil.c:625-650) for every buffered reflection of a
+			 * photon at once.  The warp works on ONE photon: lane l owns energies l, l+32, ... (T2_EU per pass) with their optical
+			 * constants and weights in registers, the history entries sit one per lane and are broadcast by shuffle, so the inner loop
+			 * is the Fresnel term and nothing else: no loads, no stores.  Weights are multiplied in the reference's order (reflection
+			 * by reflection), so they equal the immediate update bit for bit.  The survival test (any weight >= 1e-4 after each
+			 * reflection, capil.c:643-650) and the range test of the reflectivity are replayed per reflection: weights only shrink,
+			 * so "alive" holds on a prefix of the history and the first reflection that absorbs the photon is the longest such
+			 * prefix over all energies. ---------------- */
+			const bool rough = (o.sig_rough != 0.0);
+			const double sig_rough = o.sig_rough;
+			enum { U = T2_EU };
+			for (int b = 0; b < n; b++) {
+				const unsigned sl = __shfl_sync(0xffffffffu, slot, b);
+				const int nh = S.nh[sl];
+				const unsigned fl = S.flags[sl];
+				const int resume = S.resume[sl];
+				const bool final = (resume == TQ_DONE);
+				const bool winit = fl & F_WINIT;
+				const double *H = hcta + (unsigned long long)sl * (T2_HK * 4);
+				double *wscr = wcta + (unsigned long long)sl * nE;
+				double *wdst = final ? P.out.weights + (unsigned long long)S.lid[sl] * nE : wscr;
+				int k_dead = 0;		 /* reflections after which the photon is still alive (longest prefix over the passes) */
+				int first_bad = 1 << 30; /* first reflection with a reflectivity outside [0, 1] (this lane's energies) */
+				_Pragma("unroll 1") for (int e0 = 0; e0 < nE; e0 += 32 * U) {
+					int eu[U];
+					bool val[U];
+					double w[U], c_nre[U], c_nim[U], c_i2re[U], c_i2im[U], c_kr[U];
+#pragma unroll
+					for (int u = 0; u < U; u++) {
+						eu[u] = e0 + 32 * u + lane;
+						val[u] = eu[u] < nE;
+						const int ei = val[u] ? eu[u] : nE - 1;
+						c_nre[u] = __ldg(ec + EC_NRE * nE + ei);
+						c_nim[u] = __ldg(ec + EC_NIM * nE + ei);
+						c_i2re[u] = __ldg(ec + EC_I2RE * nE + ei);
+						c_i2im[u] = __ldg(ec + EC_I2IM * nE + ei);
+						c_kr[u] = rough ? __ldg(ec + EC_KR * nE + ei) : 0.0;
+						w[u] = (winit && val[u]) ? wscr[eu[u]] : 1.0;
+					}
+					int lead = 0;
+					bool still = true;
+					_Pragma("unroll 1") for (int h0 = 0; h0 < nh; h0 += 32) {
+						double h_ct = 0, h_s2 = 0, h_fs = 0, h_al = 0; /* entry h0 + lane */
+						if (h0 + lane < nh) {
+							const double2 *hp = reinterpret_cast<const double2 *>(H + (h0 + lane) * 4);
+							const double2 a = hp[0], c = hp[1];
+							h_ct = a.x; h_s2 = a.y; h_fs = c.x; h_al = c.y;
+						}
+						const int kn = (nh - h0) < 32 ? (nh - h0) : 32;
+						_Pragma("unroll 1") for (int k = 0; k < kn; k++) {
+							const double ct = __shfl_sync(0xffffffffu, h_ct, k), s2 = __shfl_sync(0xffffffffu, h_s2, k);
+							const double fs = __shfl_sync(0xffffffffu, h_fs, k);
+							double al = 0;
+							if (rough)
+								al = __shfl_sync(0xffffffffu, h_al, k);
+							bool alive_k = false, bad_k = false;
+#pragma unroll
+							for (int u = 0; u < U; u++) {
+								const double r = fresnel_rtot_fast_s2(c_nre[u], c_nim[u], c_i2re[u], c_i2im[u], ct, s2, fs);
+								if (rough) {
+									const double cr = c_kr[u] * al * sig_rough;
+									w[u] = w[u] * r * exp(-1. * cr * cr);
+								} else {
+									w[u] = w[u] * r * 1.0;
+								}
+								bad_k |= val[u] && (r < 0. || r > 1.);
+								alive_k |= val[u] && (w[u] >= 1.e-4);
+							}
+							if (bad_k && h0 + k < first_bad)
+								first_bad = h0 + k;
+							still = still && alive_k;
+							lead += still ? 1 : 0;
+						}
+					}
+					const int lead_w = __reduce_max_sync(0xffffffffu, lead);
+					k_dead = lead_w > k_dead ? lead_w : k_dead;
+#pragma unroll
+					for (int u = 0; u < U; u++)
+						if (val[u])
+							wdst[eu[u]] = w[u];
+				}
+				first_bad = __reduce_min_sync(0xffffffffu, first_bad);
+				/* reflection k_end ended the photon: reflectivity out of range (-1, tested first: capil.c:636-641) or absorbed (0) */
+				int k_end = nh, code_end = 1;
+				if (first_bad < nh && first_bad <= k_dead) {
+					k_end = first_bad;
+					code_end = -1;
+				} else if (k_dead < nh) {
+					k_end = k_dead;
+					code_end = 0;
+				}
+				int nq = resume;
+				if (lane == 0) {
+					unsigned f2 = fl | (final ? F_WOUT : F_WINIT);
+					if (k_end < nh) { /* roll the optimistic bookkeeping back to reflection k_end (it counted nh - k_end reflections too many) */
+						S.code[sl] = (signed char)code_end;
+						S.irefl[sl] = S.irefl[sl] - (nh - k_end);
+						f2 &= ~(unsigned)F_FAILHIT;
+						wst[W_REFL] += (unsigned)(k_end + 1);
+					} else {
+						wst[W_REFL] += (unsigned)nh;
+					}
+					S.flags[sl] = (unsigned char)f2;
+					S.nh[sl] = 0;
+				}
+				if (k_end < nh)
+					nq = TQ_DONE;
+				if (lane == b)
+					next = nq;
 			}
 		} else {
 			/* ---------------- NEW: fetch an id, build the start state, launch (photon.c:476-645) ---------------- */
@@ -902,10 +1070,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					S.lid[slot] = (unsigned)id; S.irefl[slot] = 0; S.ix[slot] = ix; S.iseg[slot] = iseg; S.ntrace[slot] = ntrace;
 					S.flags[slot] = (unsigned char)flags;
 					S.code[slot] = (signed char)code;
+					if (DEFER)
+						S.nh[slot] = 0;
 				}
 			}
 		}
 #undef SD
+		if (DEFER && act && next == TQ_DONE && type != TQ_ENERGY && S.nh[slot] != 0) { /* buffered reflections are evaluated before the photon is classified */
+			S.resume[slot] = (signed char)TQ_DONE;
+			next = TQ_ENERGY;
+		}
 
 		{
 			const unsigned tsum = __reduce_add_sync(0xffffffffu, t_steps);
@@ -972,7 +1146,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 static inline size_t t2_smem_bytes(int tstride)
 {
 	return 3 * (size_t)tstride * 8 + 16 * (size_t)T2_NP * 8 + (size_t)(T2_THREADS / 32) * 32 * 2 + 5 * (size_t)T2_NP * 4 + (size_t)TQ_N * T2_QCAP * 2 +
-	       2 * (size_t)T2_NP + 16 + (size_t)(T2_THREADS / 32) * 16 * 4 + 64;
+	       4 * (size_t)T2_NP + 16 + (size_t)(T2_THREADS / 32) * 16 * 4 + 64;
 }
 
 #endif
