@@ -148,6 +148,11 @@ static struct {
 	/* user table */
 	size_t n_tab;
 	double *tab_e, *tab_amu, *tab_scatf;
+	/* "# composition: Z:wt% Z:wt% ... density: rho" header of the table, when present */
+	int tab_keyed;
+	unsigned int tab_nelem;
+	int tab_iz[32];
+	double tab_wi[32], tab_density;
 } g_prov;
 
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
@@ -164,7 +169,29 @@ static void load_user_table(const char *path)
 	char line[512];
 	while (fgets(line, sizeof line, fp)) {
 		double ve, va, vs;
-		if (line[0] == '#' || sscanf(line, "%lf %lf %lf", &ve, &va, &vs) != 3)
+		if (line[0] == '#') {
+			const char *c = strstr(line, "composition:"), *dn = strstr(line, "density:");
+			if (c && dn) {
+				c += strlen("composition:");
+				unsigned int ne = 0;
+				while (c < dn && ne < 32) {
+					int z, used = 0;
+					double wt;
+					if (sscanf(c, " %d:%lf%n", &z, &wt, &used) != 2)
+						break;
+					g_prov.tab_iz[ne] = z;
+					g_prov.tab_wi[ne] = wt;
+					ne++;
+					c += used;
+				}
+				if (ne > 0 && sscanf(dn + strlen("density:"), "%lf", &g_prov.tab_density) == 1) {
+					g_prov.tab_nelem = ne;
+					g_prov.tab_keyed = 1;
+				}
+			}
+			continue;
+		}
+		if (sscanf(line, "%lf %lf %lf", &ve, &va, &vs) != 3)
 			continue;
 		if (n == cap) {
 			cap *= 2;
@@ -186,10 +213,14 @@ static void load_user_table(const char *path)
 
 static void resolve_provider(void)
 {
-	g_prov.provider = PCB_OPTCONST_BUILTIN;
-	const char *force = getenv("POLYCAP_B200_OPTCONST");  /* "builtin" pins the built-in model */
+	/* Without xraylib and without a table there is NO provider: the built-in approximation (five elements, calibrated at one
+	 * energy) is used only when the caller asks for it by name, POLYCAP_B200_OPTCONST=builtin. */
+	g_prov.provider = PCB_OPTCONST_NONE;
+	const char *force = getenv("POLYCAP_B200_OPTCONST");  /* "builtin" selects the built-in model */
 	const char *tab = getenv("POLYCAP_B200_OPTCONST_TABLE");
-	if (!(force && strcmp(force, "builtin") == 0)) {
+	if (force && strcmp(force, "builtin") == 0) {
+		g_prov.provider = PCB_OPTCONST_BUILTIN;
+	} else {
 		if (tab && *tab) {
 			load_user_table(tab);
 		} else {
@@ -210,9 +241,8 @@ static void resolve_provider(void)
 		}
 	}
 	if (g_prov.provider == PCB_OPTCONST_BUILTIN && !getenv("POLYCAP_B200_QUIET"))
-		fprintf(stderr, "polycap-b200: xraylib not found -- using the BUILT-IN APPROXIMATE optical constants "
-				"(B,O,Na,Al,Si; anchored at the 10 keV SiO2 golden). Set POLYCAP_B200_OPTCONST_TABLE "
-				"to supply 'E amu scatf' rows.\n");
+		fprintf(stderr, "polycap-b200: POLYCAP_B200_OPTCONST=builtin -- using the BUILT-IN APPROXIMATE optical constants "
+				"(B,O,Na,Al,Si; anchored at the 10 keV SiO2 golden), not xraylib.\n");
 	g_prov.resolved = 1;
 }
 
@@ -227,7 +257,8 @@ const char *pcb_optconst_provider_name(void)
 	switch (pcb_optconst_active_provider()) {
 	case PCB_OPTCONST_XRAYLIB: return "xraylib";
 	case PCB_OPTCONST_USER_TABLE: return "user-table";
-	default: return "builtin-approx";
+	case PCB_OPTCONST_BUILTIN: return "builtin-approx";
+	default: return "none";
 	}
 }
 
@@ -245,6 +276,20 @@ int pcb_optconst_compound(unsigned int nelem, const int *iz, const double *wi, d
 			  unsigned long n_energies, const double *energies, double *amu, double *scatf)
 {
 	int prov = pcb_optconst_active_provider();
+	if (prov == PCB_OPTCONST_NONE)
+		return -2;
+	if (prov == PCB_OPTCONST_USER_TABLE && g_prov.tab_keyed) { /* the table says which material it was computed for */
+		if (nelem != g_prov.tab_nelem || fabs(density - g_prov.tab_density) > 1e-9 * fabs(density))
+			return -3;
+		for (unsigned int j = 0; j < nelem; j++) {
+			int found = 0;
+			for (unsigned int k = 0; k < g_prov.tab_nelem; k++)
+				if (g_prov.tab_iz[k] == iz[j] && fabs(g_prov.tab_wi[k] - wi[j] * 100.0) <= 1e-6 * (1.0 + fabs(g_prov.tab_wi[k])))
+					found = 1;
+			if (!found)
+				return -3;
+		}
+	}
 	for (unsigned long i = 0; i < n_energies; i++) {
 		double e = energies[i];
 		if (prov == PCB_OPTCONST_USER_TABLE) {

@@ -9,8 +9,13 @@
  *
  *   1. dlopen("libxrl.so*") -- the real library, when it is installed;
  *   2. a user table  E[keV]  amu[1/cm]  scatf   (env POLYCAP_B200_OPTCONST_TABLE),
- *      linearly interpolated, applied at the compound level;
- *   3. a built-in approximate model: NIST-XCOM-style mass attenuation nodes
+ *      linearly interpolated, applied at the compound level; a header line
+ *      "# composition: 8:53.0 14:47.0 density: 2.23" (Z:weight-percent) keys it to one
+ *      material, and descriptions of another material are then refused;
+ *   3. ONLY ON REQUEST (env POLYCAP_B200_OPTCONST=builtin), a built-in approximate model:
+ *      without xraylib, table or that request the transport entry points fail with
+ *      POLYCAP_ERROR_UNSUPPORTED -- the reference cannot run without xraylib either.
+ *      The model: NIST-XCOM-style mass attenuation nodes
  *      (log-log interpolation, K edges kept as discontinuities) for B, O, Na, Al,
  *      Si and a closed-form anomalous-scattering term, both anchored to the
  *      reference's own 10 keV golden (tests/photon.c:75-76: scatf 0.503696,
@@ -26,6 +31,7 @@ extern "C" {
 #endif
 
 enum pcb_optconst_provider {
+	PCB_OPTCONST_NONE = -1, /* no xraylib, no table, built-in model not asked for: transport calls fail with UNSUPPORTED */
 	PCB_OPTCONST_BUILTIN = 0,
 	PCB_OPTCONST_XRAYLIB = 1,
 	PCB_OPTCONST_USER_TABLE = 2
@@ -38,7 +44,8 @@ double pcb_builtin_atomic_weight(int Z);            /* g/mol, <0 on unsupported 
 
 /* compound-level: fills amu[i] (1/cm) and scatf[i] for every energy.
  * Mirrors the accumulation order of polycap_photon_scatf (photon.c:83-92).
- * Returns 0 on success, -1 when an element is not covered by the active provider. */
+ * Returns 0 on success, -1 when an element is not covered by the active provider, -2 when there is no
+ * provider at all, -3 when the user table is keyed to another material. */
 int pcb_optconst_compound(unsigned int nelem, const int *iz, const double *wi, double density,
 			  unsigned long n_energies, const double *energies,
 			  double *amu, double *scatf);

@@ -34,6 +34,15 @@ extern "C" void pcb_energy_constants(size_t n_energies, const double *energies, 
 static std::mutex g_gpu_mutex; /* the device objects below are not re-entrant; calls are serialised */
 
 static bool quiet() { return getenv("POLYCAP_B200_QUIET") != NULL; }
+/* no optical constants for this material: which provider was asked and what the caller can do (optconst.h) */
+static void optconst_fail(polycap_error **error, const char *who)
+{
+	polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED,
+			  "%s: optical constants unavailable for this composition with provider '%s' (install xraylib, supply "
+			  "POLYCAP_B200_OPTCONST_TABLE for this material, or opt in to the built-in approximation with POLYCAP_B200_OPTCONST=builtin)",
+			  who, pcb_optconst_provider_name());
+}
+
 /* POLYCAP_B200_PHASES=1: wall-clock phases of polycap_source_get_transmission_efficiencies on stderr (tuning aid) */
 static bool phases_on() { return getenv("POLYCAP_B200_PHASES") != NULL; }
 static double now_ms()
@@ -67,7 +76,7 @@ static uint64_t fnv(uint64_t h, const void *p, size_t n)
 
 /* amu/scatf: NULL -> optical-constants provider */
 static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const double *energies, const double *amu_in, const double *scatf_in,
-				int device, polycap_error **error, const char *who)
+				int device, polycap_error **error, const char *who, int replica = 0)
 {
 	const polycap_profile *p = d->profile;
 	if (!p) {
@@ -79,10 +88,7 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 		memcpy(amu.data(), amu_in, nE * 8);
 		memcpy(scatf.data(), scatf_in, nE * 8);
 	} else if (pcb_optconst_compound(d->nelem, d->iz, d->wi, d->density, nE, energies, amu.data(), scatf.data()) != 0) {
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED,
-				  "%s: optical constants unavailable for this composition with provider '%s' (install xraylib or set "
-				  "POLYCAP_B200_OPTCONST_TABLE)",
-				  who, pcb_optconst_provider_name());
+		optconst_fail(error, who);
 		return nullptr;
 	}
 	uint64_t h = 1469598103934665603ULL;
@@ -99,6 +105,7 @@ static pcb_gpu_optic *optic_for(const polycap_description *d, size_t nE, const d
 	h = fnv(h, scatf.data(), nE * 8);
 	const int resolved = pcb_gpu_resolve_device(device); /* -1 -> POLYCAP_B200_DEVICE / current device: an optic lives on ONE device */
 	h = fnv(h, &resolved, sizeof resolved);
+	h = fnv(h, &replica, sizeof replica); /* a device listed twice in POLYCAP_B200_DEVICES gets two independent optics (testing aid) */
 	for (const char *k : {"POLYCAP_B200_EXACT_FRESNEL", "POLYCAP_B200_EXACT_CHECKS", "POLYCAP_B200_KERNEL", "POLYCAP_B200_DEFER_MIN",
 			      "POLYCAP_B200_DEFER_HK"}) { /* modes read at optic creation */
 		const char *v = getenv(k);
@@ -316,8 +323,7 @@ extern "C" void polycap_photon_scatf(polycap_photon *photon, polycap_error **err
 	photon->amu = (double *)malloc(sizeof(double) * photon->n_energies);
 	photon->scatf = (double *)malloc(sizeof(double) * photon->n_energies);
 	if (pcb_optconst_compound(d->nelem, d->iz, d->wi, d->density, photon->n_energies, photon->energies, photon->amu, photon->scatf) != 0)
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "polycap_photon_scatf: optical constants unavailable with provider '%s'",
-				  pcb_optconst_provider_name());
+		optconst_fail(error, "polycap_photon_scatf");
 }
 
 /* ------------------------------------------------------------------ small vector helpers
@@ -643,8 +649,8 @@ static std::vector<int> run_devices()
 			long v = strtol(p, &end, 10);
 			if (end == p)
 				break;
-			if (v >= 0 && v < n && std::find(out.begin(), out.end(), (int)v) == out.end() && out.size() < 16)
-				out.push_back((int)v);
+			if (v >= 0 && v < n && out.size() < 16)
+				out.push_back((int)v); /* a device may be listed more than once: each entry is an independent share (testing aid) */
 			p = (*end == ',') ? end + 1 : end;
 		}
 	}
@@ -689,47 +695,94 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
 	const double t_begin = now_ms();
-	pcb_gpu_optic *g = optic_for(d, nE, source->energies, NULL, NULL, -1, error, WHO);
-	if (!g)
-		return NULL;
-	const int dev = pcb_gpu_optic_device(g);
+	/* one device optic per device of the run (leak runs: one device) */
+	std::vector<int> devs = run_devices();
+	if (leak_calc)
+		devs.resize(1);
+	const int G = (int)devs.size();
+	std::vector<DevRun> R((size_t)G);
+	for (int k = 0; k < G; k++) {
+		const int replica = (int)std::count(devs.begin(), devs.begin() + k, devs[k]);
+		R[k].g = optic_for(d, nE, source->energies, NULL, NULL, devs[k], error, WHO, replica);
+		if (!R[k].g)
+			return NULL;
+		R[k].dev = pcb_gpu_optic_device(R[k].g);
+	}
+	pcb_gpu_optic *g = R[0].g;
+	const int dev = R[0].dev;
 	const uint64_t seed = run_seed();
 	const pcb_source_desc sd = source_desc(source);
 	const double t_optic = now_ms();
 
-	/* tallies and exit records live in one device buffer kept with the optic (no cudaMalloc / cudaFree per call) */
+	/* Per device: tallies and a record buffer in one device block kept with the optic (no cudaMalloc / cudaFree per call).  With one
+	 * device the buffer holds every record of the call; with several each holds a share and is reused from its start if it fills
+	 * up (after its downloads have drained). */
 	auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
-	const size_t o_cnt = up256(nE * 8), o_rf = o_cnt + up256(PCB_C_COUNT * 8), o_rw = o_rf + up256((size_t)want * 17 * 8),
-		     res_bytes = o_rw + up256((size_t)want * nE * 8);
-	char *d_res = (char *)pcb_gpu_optic_result(g, res_bytes);
-	double *d_sum = (double *)d_res;
-	int64_t *d_cnt = (int64_t *)(d_res + o_cnt);
-	double *d_rf = (double *)(d_res + o_rf);
-	double *d_rw = (double *)(d_res + o_rw);
-	std::vector<double> leak_all; /* concatenated leak records of counted photons */
-	int64_t n_leak_all = 0;
-	auto cleanup = [&]() {};
-	if (!d_res) {
-		polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate device memory for %d exit records -> %s", WHO, n_photons, pcb_gpu_last_error());
-		cleanup();
-		return NULL;
-	}
-	pcb_gpu_memset(dev, d_sum, 0, nE * 8, NULL);
-	pcb_gpu_memset(dev, d_cnt, 0, PCB_C_COUNT * 8, NULL);
-
-	/* id-ordered waves until `want` photons reached the exit window; the wave that holds the want-th exit is
-	 * cut right after it, so Sum(w)/started stays an unbiased estimator (source.c:745-884 redraws per slot). */
-	int64_t have = 0, next_id = 0, waves = 0;
 	const int64_t wave_bytes_per_id = 160 + 8 * (int64_t)nE;
 	const int64_t wave_max = std::max<int64_t>(4096, std::min<int64_t>((int64_t)1 << 24, ((int64_t)6 << 30) / wave_bytes_per_id));
-	/* Wave size: ids needed at the exit fraction seen so far plus three standard deviations of that estimate and of the
-	 * count itself (ids past the want-th exit are traced and discarded).  The first wave of a call uses the fraction the
-	 * previous call with the same source geometry ended with; without one it is a probe of 2*need ids. */
+	for (int k = 0; k < G; k++) {
+		DevRun &r = R[k];
+		/* every device could hold all records; only calls beyond 32 GB of records per device split the capacity */
+		r.rec_cap = (G == 1 || (double)want * (17 + (double)nE) * 8 <= 32e9) ? want : std::min<int64_t>(want, want / G + want / (2 * G) + 65536);
+		r.rec_used = 0;
+		const size_t o_cnt = up256(nE * 8), o_rf = o_cnt + up256(PCB_C_COUNT * 8), o_rw = o_rf + up256((size_t)r.rec_cap * 17 * 8),
+			     res_bytes = o_rw + up256((size_t)r.rec_cap * nE * 8);
+		char *d_res = (char *)pcb_gpu_optic_result(r.g, res_bytes);
+		void *st = d_res ? pcb_gpu_optic_stream(r.g) : NULL;
+		if (!d_res || !st) {
+			polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate device memory for %d exit records -> %s", WHO, n_photons,
+					  pcb_gpu_last_error());
+			return NULL;
+		}
+		r.d_sum = (double *)d_res;
+		r.d_cnt = (int64_t *)(d_res + o_cnt);
+		r.d_rf = (double *)(d_res + o_rf);
+		r.d_rw = (double *)(d_res + o_rw);
+		pcb_gpu_memset(r.dev, r.d_sum, 0, nE * 8, leak_calc ? NULL : st);
+		pcb_gpu_memset(r.dev, r.d_cnt, 0, PCB_C_COUNT * 8, leak_calc ? NULL : st);
+	}
+	std::vector<double> leak_all; /* concatenated leak records of counted photons */
+	int64_t n_leak_all = 0;
+
+	/* the host block whose slices are the arrays of struct _polycap_images: the devices copy their records straight into it,
+	 * wave by wave, while the next wave is traced */
+	polycap_transmission_efficiencies *eff = (polycap_transmission_efficiencies *)calloc(1, sizeof(*eff));
+	eff->images = (struct _polycap_images *)calloc(1, sizeof(struct _polycap_images));
+	struct _polycap_images *im = eff->images;
+	const size_t rf_bytes = (size_t)want * 17 * 8, rw_bytes = (size_t)want * nE * 8;
+	const ResultArena arena = arena_take(rf_bytes + rw_bytes);
+	double *stage = (double *)arena.p;
+	if (!stage) {
+		polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate host memory for %d exit records -> %s", WHO, n_photons, pcb_gpu_last_error());
+		polycap_transmission_efficiencies_free(eff);
+		return NULL;
+	}
+	auto fail = [&](bool cuda) {
+		if (cuda)
+			gpu_fail(error, WHO);
+		for (int k = 0; k < G; k++)
+			pcb_gpu_wave_download_sync(R[k].g);
+		arena_release(arena);
+		polycap_transmission_efficiencies_free(eff);
+		return (polycap_transmission_efficiencies *)NULL;
+	};
+	double *h_fields = stage, *h_weights = stage + (size_t)want * 17;
+
+	/* id-ordered waves until `want` photons reached the exit window; the wave that holds the want-th exit is cut right after it, so
+	 * Sum(w)/started stays an unbiased estimator (source.c:745-884 redraws per slot).  A wave's ids are dealt to the devices as
+	 * contiguous sub-ranges in device order, so "the want-th exit in id order" is found from the devices' exit counts: devices
+	 * before it keep all their ids, the one that holds it cuts, those after it are dropped (their ids count as not consumed). */
+	int64_t have = 0, next_id = 0, waves = 0;
+	/* Wave size: ids needed at the exit fraction seen so far plus three standard deviations of that estimate and of the count
+	 * itself (ids past the want-th exit are traced and discarded).  The first wave of a call uses the fraction the previous call
+	 * with the same source geometry ended with; without one it is a probe of 2*need ids.  Calls that return many megabytes of
+	 * records are split into up to 8 waves so that the download of one wave's records overlaps the trace of the next. */
 	uint64_t src_key = 1469598103934665603ULL;
 	for (size_t i = 0; i < sizeof sd; i++)
 		src_key = (src_key ^ ((const unsigned char *)&sd)[i]) * 1099511628211ULL;
 	int64_t est_exits = 0;
 	double exit_frac = pcb_gpu_optic_hint(g, src_key, &est_exits);
+	int64_t chunk_ids = 0;
 	const double t_alloc = now_ms();
 	while (have < want) {
 		const double t_w0 = now_ms();
@@ -741,26 +794,83 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		} else {
 			n_ids = 2 * need + 1024;
 		}
-		if (n_ids > wave_max)
-			n_ids = wave_max;
+		if (chunk_ids == 0 && exit_frac > 0) {
+			const char *ce = getenv("POLYCAP_B200_CHUNKS");
+			int64_t chunks = ce ? atoll(ce) : (int64_t)((rf_bytes + rw_bytes) / ((size_t)48 << 20));
+			chunks = std::max<int64_t>(1, std::min<int64_t>(8, chunks));
+			chunk_ids = std::max<int64_t>((n_ids + chunks - 1) / chunks, (int64_t)G * 65536);
+		}
+		if (!leak_calc && chunk_ids > 0 && n_ids > chunk_ids + chunk_ids / 4)
+			n_ids = chunk_ids;
+		if (n_ids > wave_max * G)
+			n_ids = wave_max * G;
 		int64_t used = 0, got = 0;
-		int rc;
 		if (leak_calc) {
 			double *lrec = NULL;
 			int64_t n_lrec = 0;
-			rc = pcb_gpu_run_wave_leak(g, &sd, seed, next_id, n_ids, need, d_sum, d_cnt, d_rf, d_rw, want, have, &used, &got, &lrec, &n_lrec);
+			if (n_ids > wave_max)
+				n_ids = wave_max;
+			int rc = pcb_gpu_run_wave_leak(g, &sd, seed, next_id, n_ids, need, R[0].d_sum, R[0].d_cnt, R[0].d_rf, R[0].d_rw, want, have, &used, &got, &lrec, &n_lrec);
 			if (rc == 0 && n_lrec > 0) {
 				leak_all.insert(leak_all.end(), lrec, lrec + (size_t)n_lrec * (11 + nE));
 				n_leak_all += n_lrec;
 			}
 			free(lrec);
+			if (rc)
+				return fail(true);
 		} else {
-			rc = pcb_gpu_run_wave(g, &sd, seed, next_id, n_ids, need, d_sum, d_cnt, d_rf, d_rw, want, have, NULL, &used, &got);
-		}
-		if (rc) {
-			gpu_fail(error, WHO);
-			cleanup();
-			return NULL;
+			/* phase 1 on every device: trace + rank the exit photons */
+			const int64_t per = (n_ids + G - 1) / G;
+			int64_t off = 0;
+			for (int k = 0; k < G; k++) {
+				DevRun &r = R[k];
+				r.n_ids = std::max<int64_t>(0, std::min<int64_t>(per, n_ids - off));
+				if (r.n_ids > 0 && pcb_gpu_wave_begin(r.g, &sd, seed, next_id + off, r.n_ids))
+					return fail(true);
+				off += r.n_ids;
+			}
+			n_ids = off;
+			for (int k = 0; k < G; k++) {
+				R[k].exits = 0;
+				if (R[k].n_ids > 0 && pcb_gpu_wave_count(R[k].g, &R[k].exits))
+					return fail(true);
+			}
+			/* phase 2: place the cut, tally, compact, and send the records on their way to the host */
+			for (int k = 0; k < G && got < need; k++) {
+				DevRun &r = R[k];
+				if (r.n_ids <= 0)
+					continue;
+				const bool cut_here = got + r.exits >= need;
+				const int64_t n_wanted = cut_here ? need - got : 0;
+				const int64_t n_rec = cut_here ? n_wanted : r.exits;
+				if (n_rec > r.rec_cap) {
+					polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: %" PRId64 " exit records of one wave exceed the record buffer of device %d (%" PRId64
+							  "); use more devices or fewer photons per call", WHO, n_rec, r.dev, r.rec_cap);
+					return fail(false);
+				}
+				if (r.rec_used + n_rec > r.rec_cap) { /* reuse the record buffer from its start once its downloads are done */
+					if (pcb_gpu_wave_reuse_records(r.g))
+						return fail(true);
+					r.rec_used = 0;
+				}
+				if (pcb_gpu_wave_finish(r.g, r.n_ids, n_wanted, r.d_sum, r.d_cnt, r.d_rf, r.d_rw, r.rec_cap, r.rec_used))
+					return fail(true);
+				int64_t ids_k = r.n_ids;
+				if (cut_here) {
+					int64_t ex_k = 0;
+					if (pcb_gpu_wave_result(r.g, &ids_k, &ex_k))
+						return fail(true);
+					if (ex_k != n_rec) {
+						polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: internal error: cut placed at %" PRId64 " exits, expected %" PRId64, WHO, ex_k, n_rec);
+						return fail(false);
+					}
+				}
+				if (pcb_gpu_wave_download(r.g, r.d_rf, r.d_rw, r.rec_cap, r.rec_used, n_rec, h_fields, h_weights, want, have + got))
+					return fail(true);
+				r.rec_used += n_rec;
+				got += n_rec;
+				used += ids_k;
+			}
 		}
 		next_id += used;
 		have += got;
@@ -768,12 +878,11 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		exit_frac = std::max(1e-4, (double)have / (double)next_id);
 		est_exits = have;
 		if (phases_on())
-			fprintf(stderr, "polycap-b200 phases: wave %" PRId64 ": %" PRId64 " ids launched, %" PRId64 " used, %" PRId64 " exits, %.2f ms\n", waves, n_ids, used, got,
-				now_ms() - t_w0);
+			fprintf(stderr, "polycap-b200 phases: wave %" PRId64 ": %" PRId64 " ids launched on %d device(s), %" PRId64 " used, %" PRId64 " exits, %.2f ms\n", waves,
+				n_ids, G, used, got, now_ms() - t_w0);
 		if (waves > 100000 || (next_id > ((int64_t)1 << 26) && have == 0)) {
 			polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: no photon reaches the exit window (%" PRId64 " started)", WHO, next_id);
-			cleanup();
-			return NULL;
+			return fail(false);
 		}
 	}
 
@@ -781,34 +890,31 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	const double t_waves = now_ms();
 	std::vector<double> sum(nE);
 	int64_t cnt[PCB_C_COUNT];
-	polycap_transmission_efficiencies *eff = (polycap_transmission_efficiencies *)calloc(1, sizeof(*eff));
-	eff->images = (struct _polycap_images *)calloc(1, sizeof(struct _polycap_images));
-	struct _polycap_images *im = eff->images;
-	/* device -> the pinned block whose slices are the arrays of struct _polycap_images (one DMA per block at PCIe speed) */
-	const size_t rf_bytes = (size_t)want * 17 * 8, rw_bytes = (size_t)want * nE * 8;
-	const double t_h0 = now_ms();
-	const ResultArena arena = arena_take(rf_bytes + rw_bytes);
-	double *stage = (double *)arena.p;
-	const double t_h1 = now_ms();
-	bool ok = stage != NULL && pcb_gpu_copy_to_host(dev, sum.data(), d_sum, nE * 8, NULL) == 0 &&
-		  pcb_gpu_copy_to_host(dev, cnt, d_cnt, sizeof cnt, NULL) == 0;
-	const double t_h2 = now_ms();
-	ok = ok && pcb_gpu_copy_to_host(dev, stage, d_rf, rf_bytes, NULL) == 0 &&
-	     pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, d_rw, rw_bytes, NULL) == 0;
-	if (phases_on())
-		fprintf(stderr, "polycap-b200 phases: result object %.2f ms, pinned block %.2f ms, tallies %.2f ms, records %.2f ms\n", t_h0 - t_waves, t_h1 - t_h0, t_h2 - t_h1,
-			now_ms() - t_h2);
-	cleanup();
-	if (!ok) {
-		if (stage == NULL)
-			polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate pinned host memory for %d exit records -> %s", WHO, n_photons, pcb_gpu_last_error());
-		else
-			gpu_fail(error, WHO);
-		if (arena.p)
-			arena_release(arena);
-		polycap_transmission_efficiencies_free(eff);
-		return NULL;
+	int used_peer = 0;
+	{
+		/* tallies: the per-device sums are added on the first device over peer memory (NVLink) or, without peer access, on the host */
+		std::vector<pcb_gpu_optic *> og((size_t)G);
+		std::vector<double *> ds((size_t)G);
+		std::vector<int64_t *> dc((size_t)G);
+		for (int k = 0; k < G; k++) {
+			og[k] = R[k].g;
+			ds[k] = R[k].d_sum;
+			dc[k] = R[k].d_cnt;
+		}
+		if (pcb_gpu_reduce_tallies(og.data(), ds.data(), dc.data(), G, sum.data(), cnt, &used_peer))
+			return fail(true);
 	}
+	const double t_h2 = now_ms();
+	if (leak_calc) { /* single wave buffer, default stream: one download at the end */
+		if (pcb_gpu_copy_to_host(dev, stage, R[0].d_rf, rf_bytes, NULL) || pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, R[0].d_rw, rw_bytes, NULL))
+			return fail(true);
+	}
+	for (int k = 0; k < G; k++)
+		if (pcb_gpu_wave_download_sync(R[k].g))
+			return fail(true);
+	if (phases_on())
+		fprintf(stderr, "polycap-b200 phases: tallies %.2f ms (%s), remaining record download %.2f ms\n", t_h2 - t_waves,
+			G > 1 ? (used_peer ? "peer reduce" : "host reduce") : "one device", now_ms() - t_h2);
 	{
 		std::lock_guard<std::mutex> lk(g_arena_mutex);
 		g_arena_of.emplace_back((const void *)eff, arena);
@@ -830,8 +936,8 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		im->pc_exit_nrefl[i] = (int64_t)v;
 	}
 	if (phases_on())
-		fprintf(stderr, "polycap-b200 phases: optic %.2f ms, device buffers %.2f ms, waves %.2f ms, device->host %.2f ms, record pointers %.2f ms\n", t_optic - t_begin,
-			t_alloc - t_optic, t_waves - t_alloc, t_d2h - t_waves, now_ms() - t_d2h);
+		fprintf(stderr, "polycap-b200 phases: optic %.2f ms, device buffers %.2f ms, waves %.2f ms, tallies + last download %.2f ms, record pointers %.2f ms\n",
+			t_optic - t_begin, t_alloc - t_optic, t_waves - t_alloc, t_d2h - t_waves, now_ms() - t_d2h);
 	/* leak records (source.c:799-879, 982-1031) */
 	if (leak_calc) {
 		const size_t stride = 11 + nE;
@@ -1340,8 +1446,7 @@ extern "C" bool polycap_b200_optical_constants(polycap_description *description,
 		return false;
 	}
 	if (pcb_optconst_compound(description->nelem, description->iz, description->wi, description->density, n_energies, energies, amu, scatf) != 0) {
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "polycap_b200_optical_constants: composition not covered by provider '%s'",
-				  pcb_optconst_provider_name());
+		optconst_fail(error, "polycap_b200_optical_constants");
 		return false;
 	}
 	return true;
@@ -1534,7 +1639,7 @@ extern "C" polycap_b200_session *polycap_b200_session_new(polycap_source *source
 	const size_t nE = source->n_energies;
 	std::vector<double> amu(nE), scatf(nE);
 	if (pcb_optconst_compound(d->nelem, d->iz, d->wi, d->density, nE, source->energies, amu.data(), scatf.data()) != 0) {
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: composition not covered by provider '%s'", W, pcb_optconst_provider_name());
+		optconst_fail(error, W);
 		return NULL;
 	}
 	pcb_optic_desc od = {p->nmax, p->z, p->cap, p->ext, d->sig_rough, d->n_cap, d->density, nE, source->energies, amu.data(), scatf.data()};

@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 				_Pragma("unroll 1") for (int e0 = 0; e0 < nE; e0 += 32 * U) {
 					int eu[U];
 					bool val[U];
-					double w[U], c_nre[U], c_nim[U], c_i2re[U], c_i2im[U], c_kr[U];
+					double w[U], c_nre[U], c_nim[U], c_nsum[U], c_i2re[U], c_i2im[U], c_kr[U];
 #pragma unroll
 					for (int u = 0; u < U; u++) {
 						eu[u] = e0 + 32 * u + lane;
@@ -890,10 +890,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						const int ei = val[u] ? eu[u] : nE - 1;
 						c_nre[u] = __ldg(ec + EC_NRE * nE + ei);
 						c_nim[u] = __ldg(ec + EC_NIM * nE + ei);
+						c_nsum[u] = c_nre[u] + c_nim[u];
 						c_i2re[u] = __ldg(ec + EC_I2RE * nE + ei);
 						c_i2im[u] = __ldg(ec + EC_I2IM * nE + ei);
 						c_kr[u] = rough ? __ldg(ec + EC_KR * nE + ei) : 0.0;
-						w[u] = (winit && val[u]) ? wscr[eu[u]] : 1.0;
+						/* lanes past the end of the grid work on a copy of the last energy with weight 0: never alive, and out of range only
+						 * where the last energy itself is -- no per-lane validity test inside the loop */
+						w[u] = val[u] ? (winit ? wscr[eu[u]] : 1.0) : 0.0;
 					}
 					int lead = 0;
 					bool still = true;
@@ -914,15 +917,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 							bool alive_k = false, bad_k = false;
 #pragma unroll
 							for (int u = 0; u < U; u++) {
-								const double r = fresnel_rtot_fast_s2(c_nre[u], c_nim[u], c_i2re[u], c_i2im[u], ct, s2, fs);
+								const double r = fresnel_rtot_fast_ns(c_nre[u], c_nim[u], c_nsum[u], c_i2re[u], c_i2im[u], ct, s2, fs);
 								if (rough) {
 									const double cr = c_kr[u] * al * sig_rough;
 									w[u] = w[u] * r * exp(-1. * cr * cr);
 								} else {
-									w[u] = w[u] * r * 1.0;
+									w[u] = w[u] * r; /* "* 1.0" of the reference is exact */
 								}
-								bad_k |= val[u] && (r < 0. || r > 1.);
-								alive_k |= val[u] && (w[u] >= 1.e-4);
+								bad_k |= pcb_refl_out_of_range(r);
+								alive_k |= pcb_weight_alive(w[u]);
 							}
 							if (bad_k && h0 + k < first_bad)
 								first_bad = h0 + k;

@@ -18,6 +18,9 @@ CORPUS = ("ellip", "conical", "parab", "xos1", "monocap", "cone_nan", "dubfoc")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     os.environ.setdefault("POLYCAP_B200_QUIET", "1")
+    # xraylib is absent from this image: the tests opt in to the built-in optical-constants model (oracle, reference build and
+    # product then consume the same amu/scatf tables, so parity does not depend on the provider)
+    os.environ.setdefault("POLYCAP_B200_OPTCONST", "builtin")
 
 
 @pytest.fixture(scope="session")

@@ -107,3 +107,39 @@ extern "C" long hm_obtuse_mismatches(long n)
 		if (pcb_acos_is_obtuse(v) != (acos(v) > M_PI / 2. || acos(v) < 0.)) bad++;
 	return bad;
 }
+// pcb_refl_out_of_range / pcb_weight_alive (integer compares on the high word) against the comparisons capil_reflect writes
+// (capil.c:636-650): random bit patterns, the neighbourhoods of 0, 1e-4 and 1 in ulps, signed zeros, infinities, NaNs of both signs
+extern "C" long hm_predicate_mismatches(long n)
+{
+	long bad = 0;
+	auto chk = [&](double v) {
+		if (pcb_refl_out_of_range(v) != (v < 0. || v > 1.)) bad++;
+		if (pcb_weight_alive(v) != (v >= 1.e-4)) bad++;
+	};
+	uint64_t s = 99;
+	for (long i = 0; i < n; i++) {
+		s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+		uint64_t b = s ^ (s >> 29);
+		double v;
+		memcpy(&v, &b, 8);
+		chk(v);
+		chk(uni(s));		    /* [0, 1) */
+		chk(1.e-4 * (0.5 + uni(s))); /* around the survival threshold */
+	}
+	const double centres[] = {0.0, 1.e-4, 1.0, -1.e-4, -1.0};
+	for (double c : centres) {
+		double x = c;
+		for (int k = 0; k < 600; k++) x = nextafter(x, -INFINITY);
+		for (int k = 0; k < 1200; k++, x = nextafter(x, INFINITY)) chk(x);
+	}
+	const uint64_t sp[] = {0x0000000000000000ULL, 0x8000000000000000ULL, 0x7ff0000000000000ULL, 0xfff0000000000000ULL, 0x7ff8000000000000ULL,
+			       0xfff8000000000000ULL, 0x7fffffffffffffffULL, 0xffffffffffffffffULL, 0x7ff0000000000001ULL, 0x0000000000000001ULL,
+			       0x3f1a36e2eb1c432dULL, 0x3f1a36e2eb1c432cULL, 0x3f1a36e2eb1c432eULL, 0x3f1a36e300000000ULL, 0x3f1a36e2ffffffffULL,
+			       0x3ff0000000000000ULL, 0x3ff0000000000001ULL, 0x3fefffffffffffffULL, 0x7fefffffffffffffULL};
+	for (uint64_t b : sp) {
+		double v;
+		memcpy(&v, &b, 8);
+		chk(v);
+	}
+	return bad;
+}

@@ -166,3 +166,40 @@ def test_compute_fails_loudly_without_cuda(pc):
         s.run_ids(1, 0, 10)
     with pytest.raises(RuntimeError, match="CUDA"):
         pc.Session(s)
+
+
+def _optconst_probe(env_extra, composition="{8: 53.0, 14: 47.0}"):
+    """polycap_b200_optical_constants in a fresh process (the provider is resolved once per process)"""
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if not k.startswith("POLYCAP_B200_OPTCONST")}
+    env.update(env_extra)
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import polycap_b200 as pc\n"
+            "prof = pc.Profile(pc.Profile.CONICAL, 9., 0.2065, 0.0585, 0.00035, 9.9153e-5, 1000., 0.5)\n"
+            "desc = pc.Description(prof, 0.0, 200000, %s, 2.23)\n"
+            "try:\n"
+            "    amu, scatf = desc.optical_constants([10.0])\n"
+            "    print('OK', pc.optconst_provider(), float(amu[0]), float(scatf[0]))\n"
+            "except Exception as e:\n"
+            "    print('ERR', pc.optconst_provider(), type(e).__name__, e)\n" % (ROOT, composition))
+    return subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120).stdout.strip()
+
+
+def test_builtin_optical_constants_are_opt_in(tmp_path):
+    """without xraylib the library has NO optical constants unless the caller names a provider -- the approximate
+    built-in model by POLYCAP_B200_OPTCONST=builtin, or a table; a table keyed to one material refuses another"""
+    out = _optconst_probe({})
+    if " xraylib " in out:
+        pytest.skip("xraylib is installed here")
+    assert out.startswith("ERR none"), out
+    assert "POLYCAP_B200_OPTCONST=builtin" in out
+    out = _optconst_probe({"POLYCAP_B200_OPTCONST": "builtin"})
+    assert out.startswith("OK builtin-approx"), out
+    assert abs(float(out.split()[2]) - 42.544635) < 1e-3 and abs(float(out.split()[3]) - 0.503696) < 1e-5  # tests/photon.c:75-76
+    tab = tmp_path / "sio2.tab"
+    tab.write_text("# composition: 8:53.0 14:47.0 density: 2.23\n1.0 3000.0 0.5\n10.0 42.5 0.5037\n100.0 0.4 0.5\n")
+    out = _optconst_probe({"POLYCAP_B200_OPTCONST_TABLE": str(tab)})
+    assert out.startswith("OK user-table 42.5"), out
+    out = _optconst_probe({"POLYCAP_B200_OPTCONST_TABLE": str(tab)}, composition="{8: 60.0, 14: 40.0}")
+    assert out.startswith("ERR user-table"), out

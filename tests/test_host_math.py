@@ -162,3 +162,10 @@ def test_segment_matches_oracle_bitwise(hm, harness, orc):
             hits += 1
             assert tuple(out) == (*ho.t(), *no.t())
     assert hits > 300
+
+
+def test_integer_compare_predicates_equal_the_float_comparisons(hm):
+    """pcb_refl_out_of_range(r) == (r < 0 || r > 1) and pcb_weight_alive(w) == (w >= 1e-4) for every bit pattern class"""
+    hm.hm_predicate_mismatches.restype = C.c_long
+    hm.hm_predicate_mismatches.argtypes = [C.c_long]
+    assert hm.hm_predicate_mismatches(2_000_000) == 0
