@@ -31,6 +31,8 @@ enum {
 	POLYCAP_B200_C_SEG_STEPS,       /* capillary segments visited */
 	POLYCAP_B200_C_SOLVES,          /* full ray/cone solves */
 	POLYCAP_B200_C_LAUNCHED,
+	/* 10..14: scheduler statistics of the tracer */
+	POLYCAP_B200_C_WALL_STEPS = 15, /* leak_calc = true: steps of the wall march (src/polycap-capil.c:1018-1068) */
 	POLYCAP_B200_N_COUNTERS = 16
 };
 
@@ -75,6 +77,10 @@ POLYCAP_EXTERN bool polycap_b200_photon_launch_batch_leaks(polycap_description *
 POLYCAP_EXTERN bool polycap_b200_source_run_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, bool leak_calc,
 						double *sum_weights, int64_t *counters, int8_t *status, double *rec, polycap_error **error);
 
+/* counters[POLYCAP_B200_N_COUNTERS] of the calling process's last polycap_source_get_transmission_efficiencies call (work counters for
+ * benchmarks: reflections of all photons, segments visited, wall-march steps ...); false when there was none */
+POLYCAP_EXTERN bool polycap_b200_last_run_counters(int64_t *counters);
+
 /* The start state (source.c:23-144 over the id's Philox stream) the device draws for ids [id0, id0+n_ids):
  * out[n_ids][11] = start coords(3), start direction(3), electric vector(3), source point x, y. */
 POLYCAP_EXTERN bool polycap_b200_source_sample_ids(polycap_source *source, uint64_t seed, int64_t id0, int64_t n_ids, double *out, polycap_error **error);
@@ -100,6 +106,24 @@ POLYCAP_EXTERN void polycap_b200_session_tune(polycap_b200_session *session, int
 POLYCAP_EXTERN void polycap_b200_session_timing(polycap_b200_session *session, int on);
 POLYCAP_EXTERN double polycap_b200_session_trace_ms(polycap_b200_session *session, int64_t *n_launches);
 POLYCAP_EXTERN int64_t polycap_b200_session_kernels(polycap_b200_session *session, int64_t *n_trace_kernels);
+
+/* ---- streams: the exit records of a run delivered chunk by chunk ------------------------------------------------------------
+ * polycap_source_get_transmission_efficiencies materialises n_photons x n_energies weights in one result object and counts in
+ * `int` (/root/reference/include/polycap-source.h:114-121, src/polycap-source.c:675): a 1e9-photon run with 291 energies does not
+ * fit that shape.  A stream walks the same id-ordered photon sequence (seed, ids 0, 1, 2 ...) and hands the records over in
+ * caller-sized chunks while the tallies keep accumulating on the device(s); POLYCAP_B200_DEVICES shards it like the plain call. */
+typedef struct _polycap_b200_stream polycap_b200_stream;
+POLYCAP_EXTERN polycap_b200_stream *polycap_b200_stream_new(polycap_source *source, uint64_t seed, polycap_error **error);
+POLYCAP_EXTERN void polycap_b200_stream_free(polycap_b200_stream *stream);
+/* Continues the run until max_records further photons reached the exit window (the id-ordered sequence is cut right after the last
+ * of them) or max_ids further ids have been traced (0: no limit).  Their records go to fields[17][max_records] (the 17 values of
+ * polycap_b200_source_run_ids, field-major) and weights[max_records][n_energies]; both NULL = tally only.  Returns the number of
+ * records delivered (< max_records only when max_ids ran out), -1 on error. */
+POLYCAP_EXTERN int64_t polycap_b200_stream_next(polycap_b200_stream *stream, int64_t max_records, int64_t max_ids, double *fields, double *weights,
+						polycap_error **error);
+/* running totals of the stream: photon ids consumed, sum of exit weights per energy, counters[POLYCAP_B200_N_COUNTERS] */
+POLYCAP_EXTERN bool polycap_b200_stream_totals(polycap_b200_stream *stream, int64_t *ids_consumed, double *sum_weights, int64_t *counters,
+					       polycap_error **error);
 
 /* FP64 FMA throughput of `device` in TFLOP/s (2 flops per DFMA) -- the roofline denominator */
 POLYCAP_EXTERN double polycap_b200_dfma_peak_tflops(int device, int iters);

@@ -34,7 +34,7 @@ c_int64_p = C.POINTER(C.c_int64)
 
 N_COUNTERS = 16
 COUNTER_NAMES = ("ids", "exit", "not_entered", "not_transmitted", "uncounted", "refl_exit", "refl_all", "seg_steps", "solves", "launched",
-                 "q_batches", "q_lanes", "q_empty_polls", "q_lost_races", "q_hit_batches", "q_hit_lanes")
+                 "q_batches", "q_lanes", "q_empty_polls", "q_lost_races", "q_hit_batches", "wall_steps")
 
 
 class _Vec3(C.Structure):
@@ -124,6 +124,11 @@ _session_tune = _sig("polycap_b200_session_tune", None, [_v, C.c_int, C.c_int, C
 _session_timing = _sig("polycap_b200_session_timing", None, [_v, C.c_int])
 _session_trace_ms = _sig("polycap_b200_session_trace_ms", C.c_double, [_v, c_int64_p])
 _session_kernels = _sig("polycap_b200_session_kernels", C.c_int64, [_v, c_int64_p])
+_stream_new = _sig("polycap_b200_stream_new", _v, [_v, C.c_uint64, _ErrPP])
+_stream_free = _sig("polycap_b200_stream_free", None, [_v])
+_stream_next = _sig("polycap_b200_stream_next", C.c_int64, [_v, C.c_int64, C.c_int64, c_double_p, c_double_p, _ErrPP])
+_stream_totals = _sig("polycap_b200_stream_totals", C.c_bool, [_v, c_int64_p, c_double_p, c_int64_p, _ErrPP])
+_last_run_counters = _sig("polycap_b200_last_run_counters", C.c_bool, [c_int64_p])
 _dfma_peak = _sig("polycap_b200_dfma_peak_tflops", C.c_double, [C.c_int, C.c_int])
 _selftest_division = _sig("polycap_b200_selftest_division", C.c_int64, [C.c_int, C.c_int64, C.c_uint64, C.c_int])
 
@@ -673,6 +678,52 @@ def launch_batch(description, energies, start_coords, start_direction, start_ele
     out["leaks"] = leaks
     out["leak_count"] = lcount
     return out
+
+
+def last_run_counters():
+    """work counters of this process's last Source.get_transmission_efficiencies call (dict by COUNTER_NAMES), None when there was none"""
+    cnt = np.zeros(N_COUNTERS, dtype=np.int64)
+    if not _last_run_counters(cnt.ctypes.data_as(c_int64_p)):
+        return None
+    return dict(zip(COUNTER_NAMES, cnt.tolist()))
+
+
+class Stream:
+    """Exit records of a run chunk by chunk (include/polycap_b200.h: polycap_b200_stream_*): the id-ordered photon sequence of `seed`
+    continues from call to call, the tallies accumulate on the device(s)."""
+
+    def __init__(self, source, seed=20000):
+        self._source_py = source
+        self._nE = source.n_energies()
+        e = _err()
+        self._stream = _stream_new(source._source, int(seed), C.byref(e))
+        _raise(e)
+
+    def __del__(self):
+        if getattr(self, "_stream", None):
+            _stream_free(self._stream)
+            self._stream = None
+
+    def next(self, max_records, max_ids=0, records=True):
+        """-> (fields [17][n], weights [n][nE]) of the next n <= max_records exit photons (records=False: just n, tally only)"""
+        f = np.zeros((17, max_records)) if records else None
+        w = np.zeros((max_records, self._nE)) if records else None
+        e = _err()
+        n = _stream_next(self._stream, int(max_records), int(max_ids), _dp(f) if records else None, _dp(w) if records else None, C.byref(e))
+        _raise(e)
+        if not records:
+            return n
+        return f[:, :n], w[:n]
+
+    def totals(self):
+        """-> (photon ids consumed, sum of exit weights per energy, counters dict)"""
+        ids = C.c_int64(0)
+        sw = np.zeros(self._nE)
+        cnt = np.zeros(N_COUNTERS, dtype=np.int64)
+        e = _err()
+        _stream_totals(self._stream, C.byref(ids), _dp(sw), cnt.ctypes.data_as(c_int64_p), C.byref(e))
+        _raise(e)
+        return ids.value, sw, dict(zip(COUNTER_NAMES, cnt.tolist()))
 
 
 class Session:

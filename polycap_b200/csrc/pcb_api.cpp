@@ -659,6 +659,18 @@ static std::vector<int> run_devices()
 	return out;
 }
 
+static int64_t g_last_counters[PCB_C_COUNT];
+static bool g_have_last_counters = false;
+
+extern "C" bool polycap_b200_last_run_counters(int64_t *counters)
+{
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	if (!counters || !g_have_last_counters)
+		return false;
+	memcpy(counters, g_last_counters, sizeof g_last_counters);
+	return true;
+}
+
 struct DevRun { /* one device's share of a run */
 	pcb_gpu_optic *g;
 	int dev;
@@ -668,6 +680,76 @@ struct DevRun { /* one device's share of a run */
 	int64_t rec_cap, rec_used;
 	int64_t n_ids, exits; /* current wave */
 };
+
+/* One id-ordered wave over the devices of a run, without leaks: ids [id0, id0 + *n_ids) are dealt to the devices as contiguous
+ * sub-ranges in device order; phase 1 traces and ranks the exit photons on every device, then the "need-th exit in id order" is
+ * found from the devices' exit counts: devices before it keep all their ids, the one that holds it cuts, those after it are
+ * dropped (their ids count as not consumed).  Records of the kept ids go to host arrays laid out [17][host_cap] / [host_cap][nE] at
+ * record host_base, downloaded on each device's copy stream while the caller launches the next wave.
+ * Returns 0, 1 = CUDA failure (pcb_gpu_last_error), 2 = error already set. */
+static int plain_wave(std::vector<DevRun> &R, const pcb_source_desc &sd, uint64_t seed, int64_t id0, int64_t *n_ids, int64_t need, double *h_fields,
+		      double *h_weights, int64_t host_cap, int64_t host_base, int64_t *used_out, int64_t *got_out, polycap_error **error, const char *WHO)
+{
+	const int G = (int)R.size();
+	int64_t used = 0, got = 0;
+	/* phase 1 on every device: trace + rank the exit photons */
+	const int64_t per = (*n_ids + G - 1) / G;
+	int64_t off = 0;
+	for (int k = 0; k < G; k++) {
+		DevRun &r = R[k];
+		r.n_ids = std::max<int64_t>(0, std::min<int64_t>(per, *n_ids - off));
+		if (r.n_ids > 0 && pcb_gpu_wave_begin(r.g, &sd, seed, id0 + off, r.n_ids))
+			return 1;
+		off += r.n_ids;
+	}
+	*n_ids = off;
+	for (int k = 0; k < G; k++) {
+		R[k].exits = 0;
+		if (R[k].n_ids > 0 && pcb_gpu_wave_count(R[k].g, &R[k].exits))
+			return 1;
+	}
+	/* phase 2: place the cut, tally, compact, and send the records on their way to the host */
+	for (int k = 0; k < G && got < need; k++) {
+		DevRun &r = R[k];
+		if (r.n_ids <= 0)
+			continue;
+		const bool cut_here = got + r.exits >= need;
+		const int64_t n_wanted = cut_here ? need - got : 0;
+		const int64_t n_rec = cut_here ? n_wanted : r.exits;
+		const bool records = h_fields != NULL; /* tally-only callers keep no records: nothing is compacted or downloaded */
+		if (records && n_rec > r.rec_cap) {
+			polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: %" PRId64 " exit records of one wave exceed the record buffer of device %d (%" PRId64
+					  "); use more devices or fewer photons per call", WHO, n_rec, r.dev, r.rec_cap);
+			return 2;
+		}
+		if (records && r.rec_used + n_rec > r.rec_cap) { /* reuse the record buffer from its start once its downloads are done */
+			if (pcb_gpu_wave_reuse_records(r.g))
+				return 1;
+			r.rec_used = 0;
+		}
+		if (pcb_gpu_wave_finish(r.g, r.n_ids, n_wanted, r.d_sum, r.d_cnt, records ? r.d_rf : NULL, records ? r.d_rw : NULL, r.rec_cap, r.rec_used))
+			return 1;
+		int64_t ids_k = r.n_ids;
+		if (cut_here) {
+			int64_t ex_k = 0;
+			if (pcb_gpu_wave_result(r.g, &ids_k, &ex_k))
+				return 1;
+			if (ex_k != n_rec) {
+				polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: internal error: cut placed at %" PRId64 " exits, expected %" PRId64, WHO, ex_k, n_rec);
+				return 2;
+			}
+		}
+		if (records && pcb_gpu_wave_download(r.g, r.d_rf, r.d_rw, r.rec_cap, r.rec_used, n_rec, h_fields, h_weights, host_cap, host_base + got))
+			return 1;
+		if (records)
+			r.rec_used += n_rec;
+		got += n_rec;
+		used += ids_k;
+	}
+	*used_out = used;
+	*got_out = got;
+	return 0;
+}
 
 extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_efficiencies(polycap_source *source, int max_threads, int n_photons,
 											    bool leak_calc, polycap_progress_monitor *progress_monitor,
@@ -782,7 +864,7 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		src_key = (src_key ^ ((const unsigned char *)&sd)[i]) * 1099511628211ULL;
 	int64_t est_exits = 0;
 	double exit_frac = pcb_gpu_optic_hint(g, src_key, &est_exits);
-	int64_t chunk_ids = 0;
+	int64_t chunk_ids = 0, leak_shrink = 1;
 	const double t_alloc = now_ms();
 	while (have < want) {
 		const double t_w0 = now_ms();
@@ -808,9 +890,20 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		if (leak_calc) {
 			double *lrec = NULL;
 			int64_t n_lrec = 0;
-			if (n_ids > wave_max)
-				n_ids = wave_max;
+			/* a leak wave also holds ~24 leak records of 11+nE doubles per id (pcb_leak.cu): its own bytes-per-id budget, 8 GB per wave;
+			 * a wave whose record pool still overflows (thin walls, hard photons) is retried with half the ids */
+			const int64_t leak_bytes_per_id = wave_bytes_per_id + 24 * (11 + (int64_t)nE) * 8;
+			const int64_t leak_wave_max = std::max<int64_t>(1024, std::min<int64_t>(wave_max, ((int64_t)8 << 30) / leak_bytes_per_id));
+			if (n_ids > leak_wave_max)
+				n_ids = leak_wave_max;
+			if (leak_shrink > 1)
+				n_ids = std::max<int64_t>(256, n_ids / leak_shrink);
 			int rc = pcb_gpu_run_wave_leak(g, &sd, seed, next_id, n_ids, need, R[0].d_sum, R[0].d_cnt, R[0].d_rf, R[0].d_rw, want, have, &used, &got, &lrec, &n_lrec);
+			if (rc == -2 && n_ids > 256) {
+				free(lrec);
+				leak_shrink *= 2;
+				continue;
+			}
 			if (rc == 0 && n_lrec > 0) {
 				leak_all.insert(leak_all.end(), lrec, lrec + (size_t)n_lrec * (11 + nE));
 				n_leak_all += n_lrec;
@@ -819,58 +912,9 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 			if (rc)
 				return fail(true);
 		} else {
-			/* phase 1 on every device: trace + rank the exit photons */
-			const int64_t per = (n_ids + G - 1) / G;
-			int64_t off = 0;
-			for (int k = 0; k < G; k++) {
-				DevRun &r = R[k];
-				r.n_ids = std::max<int64_t>(0, std::min<int64_t>(per, n_ids - off));
-				if (r.n_ids > 0 && pcb_gpu_wave_begin(r.g, &sd, seed, next_id + off, r.n_ids))
-					return fail(true);
-				off += r.n_ids;
-			}
-			n_ids = off;
-			for (int k = 0; k < G; k++) {
-				R[k].exits = 0;
-				if (R[k].n_ids > 0 && pcb_gpu_wave_count(R[k].g, &R[k].exits))
-					return fail(true);
-			}
-			/* phase 2: place the cut, tally, compact, and send the records on their way to the host */
-			for (int k = 0; k < G && got < need; k++) {
-				DevRun &r = R[k];
-				if (r.n_ids <= 0)
-					continue;
-				const bool cut_here = got + r.exits >= need;
-				const int64_t n_wanted = cut_here ? need - got : 0;
-				const int64_t n_rec = cut_here ? n_wanted : r.exits;
-				if (n_rec > r.rec_cap) {
-					polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: %" PRId64 " exit records of one wave exceed the record buffer of device %d (%" PRId64
-							  "); use more devices or fewer photons per call", WHO, n_rec, r.dev, r.rec_cap);
-					return fail(false);
-				}
-				if (r.rec_used + n_rec > r.rec_cap) { /* reuse the record buffer from its start once its downloads are done */
-					if (pcb_gpu_wave_reuse_records(r.g))
-						return fail(true);
-					r.rec_used = 0;
-				}
-				if (pcb_gpu_wave_finish(r.g, r.n_ids, n_wanted, r.d_sum, r.d_cnt, r.d_rf, r.d_rw, r.rec_cap, r.rec_used))
-					return fail(true);
-				int64_t ids_k = r.n_ids;
-				if (cut_here) {
-					int64_t ex_k = 0;
-					if (pcb_gpu_wave_result(r.g, &ids_k, &ex_k))
-						return fail(true);
-					if (ex_k != n_rec) {
-						polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: internal error: cut placed at %" PRId64 " exits, expected %" PRId64, WHO, ex_k, n_rec);
-						return fail(false);
-					}
-				}
-				if (pcb_gpu_wave_download(r.g, r.d_rf, r.d_rw, r.rec_cap, r.rec_used, n_rec, h_fields, h_weights, want, have + got))
-					return fail(true);
-				r.rec_used += n_rec;
-				got += n_rec;
-				used += ids_k;
-			}
+			const int prc = plain_wave(R, sd, seed, next_id, &n_ids, need, h_fields, h_weights, want, have, &used, &got, error, WHO);
+			if (prc)
+				return fail(prc == 1);
 		}
 		next_id += used;
 		have += got;
@@ -904,6 +948,8 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		if (pcb_gpu_reduce_tallies(og.data(), ds.data(), dc.data(), G, sum.data(), cnt, &used_peer))
 			return fail(true);
 	}
+	memcpy(g_last_counters, cnt, sizeof g_last_counters);
+	g_have_last_counters = true;
 	const double t_h2 = now_ms();
 	if (leak_calc) { /* single wave buffer, default stream: one download at the end */
 		if (pcb_gpu_copy_to_host(dev, stage, R[0].d_rf, rf_bytes, NULL) || pcb_gpu_copy_to_host(dev, stage + (size_t)want * 17, R[0].d_rw, rw_bytes, NULL))
@@ -1655,6 +1701,210 @@ extern "C" polycap_b200_session *polycap_b200_session_new(polycap_source *source
 	s->seed = seed;
 	s->device = pcb_gpu_optic_device(g);
 	return s;
+}
+
+/* ---- streams ---- */
+struct _polycap_b200_stream {
+	std::vector<DevRun> R;     /* own optics (not the cache's: they must outlive other calls) and own device buffers */
+	std::vector<void *> d_mem; /* per device: tallies + record buffer */
+	pcb_source_desc sd;
+	uint64_t seed;
+	size_t nE;
+	int64_t next_id, exits, rec_cap;
+};
+
+static pcb_gpu_optic *own_optic(polycap_source *source, int device, polycap_error **error, const char *W)
+{
+	const polycap_description *d = source->description;
+	const polycap_profile *p = d->profile;
+	const size_t nE = source->n_energies;
+	std::vector<double> amu(nE), scatf(nE);
+	if (pcb_optconst_compound(d->nelem, d->iz, d->wi, d->density, nE, source->energies, amu.data(), scatf.data()) != 0) {
+		optconst_fail(error, W);
+		return NULL;
+	}
+	pcb_optic_desc od = {p->nmax, p->z, p->cap, p->ext, d->sig_rough, d->n_cap, d->density, nE, source->energies, amu.data(), scatf.data()};
+	pcb_gpu_optic *g = pcb_gpu_optic_create(device, &od);
+	if (!g)
+		polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: no usable CUDA device (%s); this library has no CPU path", W, pcb_gpu_last_error());
+	return g;
+}
+
+static void stream_release(polycap_b200_stream *st)
+{
+	for (size_t k = 0; k < st->R.size(); k++) {
+		if (st->R[k].g) {
+			pcb_gpu_wave_download_sync(st->R[k].g);
+			if (k < st->d_mem.size() && st->d_mem[k])
+				pcb_gpu_free(st->R[k].dev, st->d_mem[k]);
+			pcb_gpu_optic_destroy(st->R[k].g);
+		}
+	}
+	delete st;
+}
+
+extern "C" polycap_b200_stream *polycap_b200_stream_new(polycap_source *source, uint64_t seed, polycap_error **error)
+{
+	static const char *W = "polycap_b200_stream_new";
+	if (!check_source(source, error, W))
+		return NULL;
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	polycap_b200_stream *st = new _polycap_b200_stream();
+	st->sd = source_desc(source);
+	st->seed = seed;
+	st->nE = source->n_energies;
+	st->next_id = st->exits = st->rec_cap = 0;
+	const std::vector<int> devs = run_devices();
+	for (int dv : devs) {
+		DevRun r{};
+		r.g = own_optic(source, dv, error, W);
+		if (!r.g || !pcb_gpu_optic_stream(r.g)) {
+			if (r.g) {
+				gpu_fail(error, W);
+				pcb_gpu_optic_destroy(r.g);
+			}
+			stream_release(st);
+			return NULL;
+		}
+		r.dev = pcb_gpu_optic_device(r.g);
+		st->R.push_back(r);
+		st->d_mem.push_back(NULL);
+	}
+	return st;
+}
+
+extern "C" void polycap_b200_stream_free(polycap_b200_stream *stream)
+{
+	if (!stream)
+		return;
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	stream_release(stream);
+}
+
+/* (re)allocates the per-device block: tallies (kept) + a record buffer of rec_cap records */
+static bool stream_buffers(polycap_b200_stream *st, int64_t rec_cap)
+{
+	auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+	const size_t nE = st->nE;
+	const size_t o_cnt = up256(nE * 8), o_rf = o_cnt + up256(PCB_C_COUNT * 8);
+	if (rec_cap <= st->rec_cap && st->d_mem[0])
+		return true;
+	for (size_t k = 0; k < st->R.size(); k++) {
+		DevRun &r = st->R[k];
+		const size_t o_rw = o_rf + up256((size_t)rec_cap * 17 * 8), bytes = o_rw + up256((size_t)rec_cap * nE * 8);
+		char *nw = (char *)pcb_gpu_malloc(r.dev, bytes);
+		if (!nw)
+			return false;
+		void *strm = pcb_gpu_optic_stream(r.g);
+		pcb_gpu_wave_download_sync(r.g);
+		if (st->d_mem[k]) { /* carry the tallies over */
+			if (pcb_gpu_sync(r.dev, strm) || pcb_gpu_copy_dev(r.dev, nw, st->d_mem[k], o_rf, strm))
+				return false;
+			pcb_gpu_sync(r.dev, strm);
+			pcb_gpu_free(r.dev, st->d_mem[k]);
+		} else {
+			pcb_gpu_memset(r.dev, nw, 0, o_rf, strm);
+		}
+		st->d_mem[k] = nw;
+		r.d_sum = (double *)nw;
+		r.d_cnt = (int64_t *)(nw + o_cnt);
+		r.d_rf = (double *)(nw + o_rf);
+		r.d_rw = (double *)(nw + o_rw);
+		r.rec_cap = rec_cap;
+		r.rec_used = 0;
+	}
+	st->rec_cap = rec_cap;
+	return true;
+}
+
+extern "C" int64_t polycap_b200_stream_next(polycap_b200_stream *stream, int64_t max_records, int64_t max_ids, double *fields, double *weights,
+					    polycap_error **error)
+{
+	static const char *W = "polycap_b200_stream_next";
+	if (!stream || max_records < 1 || max_ids < 0 || (fields == NULL) != (weights == NULL)) {
+		polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: stream cannot be NULL, max_records must be >= 1, max_ids >= 0, fields and weights both or neither", W);
+		return -1;
+	}
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	polycap_b200_stream *st = stream;
+	const int G = (int)st->R.size();
+	const int64_t wave_bytes_per_id = 160 + 8 * (int64_t)st->nE;
+	const int64_t wave_max = std::max<int64_t>(4096, std::min<int64_t>((int64_t)1 << 24, ((int64_t)6 << 30) / wave_bytes_per_id));
+	/* tally-only chunks still rank and compact nothing: a one-record buffer is enough for them */
+	if (!stream_buffers(st, fields ? max_records : std::max<int64_t>(st->rec_cap, 1))) {
+		polycap_set_error(error, POLYCAP_ERROR_MEMORY, "%s: could not allocate device memory for %" PRId64 " records -> %s", W, max_records, pcb_gpu_last_error());
+		return -1;
+	}
+	int64_t have = 0, ids_done = 0, waves = 0;
+	while (have < max_records && (max_ids == 0 || ids_done < max_ids)) {
+		const int64_t need = max_records - have;
+		int64_t n_ids;
+		if (st->next_id > 0 && st->exits > 0) {
+			const double frac = (double)st->exits / (double)st->next_id;
+			const double margin = std::min(0.25, 3.0 * sqrt(1.0 / (double)st->exits + 1.0 / (double)need) + 0.002);
+			n_ids = (int64_t)((double)need / frac * (1.0 + margin)) + 256;
+		} else {
+			n_ids = 2 * need + 1024;
+		}
+		n_ids = std::min<int64_t>(n_ids, wave_max * G);
+		if (max_ids > 0)
+			n_ids = std::min<int64_t>(n_ids, max_ids - ids_done);
+		int64_t used = 0, got = 0;
+		/* tally-only: no cut is needed to bound a buffer, but the id-ordered cut keeps "n exits" semantics identical */
+		const int prc = plain_wave(st->R, st->sd, st->seed, st->next_id, &n_ids, need, fields, weights, max_records, have, &used, &got, error, W);
+		if (prc) {
+			if (prc == 1)
+				gpu_fail(error, W);
+			for (int k = 0; k < G; k++)
+				pcb_gpu_wave_download_sync(st->R[k].g);
+			return -1;
+		}
+		st->next_id += used;
+		st->exits += got;
+		have += got;
+		ids_done += used;
+		if (++waves > 100000 || (used == 0 && got == 0)) {
+			polycap_set_error(error, POLYCAP_ERROR_RUNTIME, "%s: the run does not advance (%" PRId64 " ids so far)", W, st->next_id);
+			return -1;
+		}
+	}
+	for (int k = 0; k < G; k++)
+		if (pcb_gpu_wave_download_sync(st->R[k].g)) {
+			gpu_fail(error, W);
+			return -1;
+		}
+	return have;
+}
+
+extern "C" bool polycap_b200_stream_totals(polycap_b200_stream *stream, int64_t *ids_consumed, double *sum_weights, int64_t *counters, polycap_error **error)
+{
+	static const char *W = "polycap_b200_stream_totals";
+	if (!stream || !sum_weights || !counters) {
+		polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: NULL argument", W);
+		return false;
+	}
+	std::lock_guard<std::mutex> lock(g_gpu_mutex);
+	const int G = (int)stream->R.size();
+	if (ids_consumed)
+		*ids_consumed = stream->next_id;
+	if (!stream->d_mem[0]) { /* nothing traced yet */
+		memset(sum_weights, 0, stream->nE * 8);
+		memset(counters, 0, PCB_C_COUNT * 8);
+		return true;
+	}
+	std::vector<pcb_gpu_optic *> og((size_t)G);
+	std::vector<double *> ds((size_t)G);
+	std::vector<int64_t *> dc((size_t)G);
+	for (int k = 0; k < G; k++) {
+		og[k] = stream->R[k].g;
+		ds[k] = stream->R[k].d_sum;
+		dc[k] = stream->R[k].d_cnt;
+	}
+	if (pcb_gpu_reduce_tallies(og.data(), ds.data(), dc.data(), G, sum_weights, counters, NULL)) {
+		gpu_fail(error, W);
+		return false;
+	}
+	return true;
 }
 
 extern "C" void polycap_b200_session_free(polycap_b200_session *session)

@@ -40,6 +40,8 @@ enum {
 	PCB_C_SEG_STEPS,        /* segments visited */
 	PCB_C_SOLVES,           /* full quadratic solves */
 	PCB_C_LAUNCHED,
+	/* 10..14: scheduler statistics of the task-queue tracer (batches, lanes, empty polls, lost races, HIT batches) */
+	PCB_C_WALL_STEPS = 15,  /* leak runs: steps of the wall march (capil.c:1018-1068) */
 	PCB_C_COUNT = 16
 };
 
@@ -127,6 +129,7 @@ void pcb_gpu_host_free(void *p);
 int pcb_gpu_memset(int device, void *p, int v, size_t bytes, void *stream);
 int pcb_gpu_copy_to_host(int device, void *dst, const void *src_dev, size_t bytes, void *stream);
 int pcb_gpu_sync(int device, void *stream);
+int pcb_gpu_copy_dev(int device, void *dst_dev, const void *src_dev, size_t bytes, void *stream); /* asynchronous, same device */
 
 /* FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), timed with CUDA events */
 double pcb_gpu_dfma_peak(int device, int iters);

@@ -1132,8 +1132,8 @@ extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *co
 	std::vector<int8_t> st((size_t)n);
 	std::vector<int> ir((size_t)n), ln((size_t)n);
 	std::vector<double> f((size_t)n * 11);
-	int64_t refl = 0;
-	if (pcb_leak_run(&v, nullptr, 0, 0, n, coords, dir, ev, st.data(), ir.data(), f.data(), weights, ln.data(), leak_rec, n_leak_rec, &refl)) {
+	int64_t work[2] = {0, 0};
+	if (pcb_leak_run(&v, nullptr, 0, 0, n, coords, dir, ev, st.data(), ir.data(), f.data(), weights, ln.data(), leak_rec, n_leak_rec, work)) {
 		g_last_error = pcb_leak_last_error();
 		return -1;
 	}
@@ -1154,8 +1154,9 @@ extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *co
 	if (counters) {
 		memset(counters, 0, PCB_C_COUNT * 8);
 		counters[PCB_C_IDS] = n;
-		counters[PCB_C_REFL_ALL] = refl;
+		counters[PCB_C_REFL_ALL] = work[0];
 		counters[PCB_C_LAUNCHED] = n;
+		counters[PCB_C_WALL_STEPS] = work[1];
 	}
 	return 0;
 }
@@ -1178,17 +1179,18 @@ extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s,
 	std::vector<int> ir((size_t)n_ids), ln((size_t)n_ids);
 	std::vector<double> f((size_t)n_ids * 17), w((size_t)n_ids * nE);
 	double *recs = nullptr;
-	int64_t nrec = 0, refl = 0;
-	if (pcb_leak_run(&v, s, seed, id0, n_ids, nullptr, nullptr, nullptr, st.data(), ir.data(), f.data(), w.data(), ln.data(), &recs, &nrec, &refl)) {
+	int64_t nrec = 0, work[2] = {0, 0};
+	if (int lrc = pcb_leak_run(&v, s, seed, id0, n_ids, nullptr, nullptr, nullptr, st.data(), ir.data(), f.data(), w.data(), ln.data(), &recs, &nrec, work)) {
 		g_last_error = pcb_leak_last_error();
-		return -1;
+		return lrc; /* -2: record pool full, the caller retries with a smaller wave */
 	}
 	g->n_kernels++;
 	/* same id-ordered post-processing as the plain path, over the leak kernel's dense outputs */
 	cudaStream_t stream = 0;
 	PcbWorkCounters wc{};
-	wc.reflections = (unsigned long long)refl;
+	wc.reflections = (unsigned long long)work[0];
 	wc.launched = (unsigned long long)n_ids;
+	wc.dbg[5] = (unsigned long long)work[1]; /* -> counters[PCB_C_WALL_STEPS] */
 	bool ok = cudaMemcpy(g->d_status, st.data(), (size_t)n_ids, cudaMemcpyHostToDevice) == cudaSuccess &&
 		  cudaMemcpy(g->d_irefl, ir.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
 		  cudaMemcpy(g->d_fields, f.data(), f.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -1290,6 +1292,12 @@ extern "C" int pcb_gpu_copy_to_host(int device, void *dst, const void *src, size
 	CK(cudaSetDevice(pick_device(device)));
 	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
 	CK(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+extern "C" int pcb_gpu_copy_dev(int device, void *dst, const void *src, size_t bytes, void *stream)
+{
+	CK(cudaSetDevice(pick_device(device)));
+	CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
 	return 0;
 }
 extern "C" int pcb_gpu_sync(int device, void *stream)

@@ -35,7 +35,7 @@
 #define LK_REC_CAP 2048  /* leak records */
 #define LK_THREADS 128
 
-enum { LK_ERR_DEPTH = 1, LK_ERR_RECORDS = 2 };
+enum { LK_ERR_DEPTH = 1, LK_ERR_RECORDS = 2, LK_ERR_POOL = 4 }; /* RECORDS: one photon exceeds LK_REC_CAP leaks; POOL: the wave's record pool is full */
 
 struct LkCtx {
 	int nmax, nE, mono, monotonic;
@@ -61,10 +61,46 @@ struct LkFrame {
 enum { CONT_TRACE = 0, CONT_FACE = 1 };
 
 struct LkOut {
-	double *rec;    /* this thread's strip: LK_REC_CAP x (11+nE) */
+	double *rec;    /* this thread's strip: cap x (11+nE) */
 	int nrec;
 	int err;
+	int cap;        /* records the strip holds */
+	int depth;      /* frames this thread's stack holds */
+	/* pool of full-size workspaces (LK_DEPTH frames, LK_REC_CAP records) a photon moves to when it outgrows the thread's small one */
+	LkFrame *big_frames;
+	double *big_arena, *big_rec;
+	unsigned long long *big_next;
+	unsigned long long big_n;
 };
+
+/* The photon's nesting is about to exceed the thread's small workspace: move its frames [0, sp], their weight vectors and its
+ * records to a full-size workspace from the pool and carry on there.  false: already full-size, or the pool is used up. */
+__device__ bool lk_grow(const LkCtx &c, LkOut &o, LkFrame *&fr, double *&arena, int sp)
+{
+	if (o.depth >= LK_DEPTH || !o.big_next)
+		return false;
+	const unsigned long long idx = atomicAdd(o.big_next, 1ULL);
+	if (idx >= o.big_n)
+		return false;
+	const size_t nE = (size_t)c.nE, stride = 11 + nE;
+	LkFrame *nf = o.big_frames + idx * (unsigned long long)LK_DEPTH;
+	double *na = o.big_arena + idx * (unsigned long long)(LK_DEPTH + 1) * nE;
+	double *nr = o.big_rec + idx * (unsigned long long)LK_REC_CAP * stride;
+	for (size_t k = 0; k < (size_t)(sp + 1) * nE; k++)
+		na[k] = arena[k];
+	for (int k = 0; k <= sp; k++) {
+		nf[k] = fr[k];
+		nf[k].w = na + (fr[k].w - arena);
+	}
+	for (size_t k = 0; k < (size_t)o.nrec * stride; k++)
+		nr[k] = o.rec[k];
+	fr = nf;
+	arena = na;
+	o.rec = nr;
+	o.cap = LK_REC_CAP;
+	o.depth = LK_DEPTH;
+	return true;
+}
 
 __device__ __forceinline__ int lk_z_index(const LkCtx &c, double zq) /* last i < nmax with z[i] <= zq, 0 when none */
 {
@@ -114,7 +150,7 @@ __device__ __forceinline__ V3 lk_propagate(const V3 &p, const V3 &d, double zt)
 
 __device__ void lk_append(const LkCtx &c, LkOut &o, int kind, const V3 &co, const V3 &di, const V3 &el, long long nrefl, const double *w)
 {
-	if (o.nrec >= LK_REC_CAP) {
+	if (o.nrec >= o.cap) {
 		o.err |= LK_ERR_RECORDS;
 		return;
 	}
@@ -242,7 +278,7 @@ __device__ __forceinline__ int lk_segment_checked(const V3 &c0, const V3 &c1, do
 }
 
 /* capil.c:896-1194; ed is normalised in place like the reference does with photon->exit_direction */
-__device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel, int &r_cntr, int &q_cntr)
+__device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel, int &r_cntr, int &q_cntr, unsigned long long &n_steps)
 {
 	const int nm = c.nmax;
 	d_travel = 0.;
@@ -282,6 +318,7 @@ __device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_tra
 		double dist = 0;
 		for (;;) {
 			do { /* march in steps of a tenth of the bore radius until the hex cell changes (capil.c:1018-1068) */
+				n_steps++;
 				dist += c.cap[z_id] / 10.;
 				p0.x = ec.x + dist * ed.x;
 				p0.y = ec.y + dist * ed.y;
@@ -419,9 +456,9 @@ struct LkResult {
 };
 
 /* polycap_photon_launch with leak_calc = true (photon.c:390-955), iterative over an explicit frame stack.
- * `arena` holds (LK_DEPTH+1) weight vectors of nE doubles; arena[0..nE) ends up with the primary's weights. */
-__device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, double d_travel0, LkFrame *fr, double *arena, LkOut &out, LkResult &res,
-			  unsigned long long &n_refl_events)
+ * `arena` holds (out.depth+1) weight vectors of nE doubles; arena[0..nE) ends up with the primary's weights. */
+__device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, double d_travel0, LkFrame *&fr, double *&arena, LkOut &out, LkResult &res,
+			  unsigned long long &n_refl_events, unsigned long long &n_wall_steps)
 {
 	const int nm = c.nmax, nE = c.nE;
 	int sp = 0;
@@ -491,7 +528,7 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 			} else { /* photon.c:673-887 */
 				double d_wall = 0;
 				int r_cntr, q_cntr;
-				int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr);
+				int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr, n_wall_steps);
 				if (wall_trace <= 0) {
 					ret = -1;
 					state = S_FINISH;
@@ -565,17 +602,21 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 			}
 			double d_wall = 0;
 			int r_cntr = 0, q_cntr = 0;
-			int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr);
+			int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr, n_wall_steps);
 			if (wall_trace <= 0) {
 				riesc = -1;
 				state = S_AFTER_REFLECT;
 				continue;
 			}
-			if (sp + 1 >= LK_DEPTH) {
-				out.err |= LK_ERR_DEPTH;
-				riesc = -1;
-				state = S_AFTER_REFLECT;
-				continue;
+			if (sp + 1 >= out.depth) {
+				if (lk_grow(c, out, fr, arena, sp)) {
+					f = &fr[sp];
+				} else {
+					out.err |= LK_ERR_DEPTH;
+					riesc = -1;
+					state = S_AFTER_REFLECT;
+					continue;
+				}
 			}
 			double *w_leak = arena + (size_t)(sp + 1) * nE;
 			ReflGeom g;
@@ -745,9 +786,17 @@ struct LkParams {
 	const double *rin;        /* replay: coords[n][3], dir[n][3], ev[n][3] */
 	unsigned long long id0, n;
 	unsigned long long *next; /* work counter */
-	double *arena;            /* [threads][(LK_DEPTH+1)*nE] */
-	LkFrame *frames;          /* [threads][LK_DEPTH] */
-	double *rec;              /* [threads][LK_REC_CAP*(11+nE)] scratch strips */
+	int depth, rec_cap;       /* per-thread capacities of this launch: frames, leak records */
+	const unsigned long long *todo; /* second launch: the ids (local indices) the first one could not hold; NULL: all of [0, n) */
+	unsigned long long n_todo;
+	unsigned long long *retry;      /* first launch: ids whose nesting depth / record count exceeded the small capacities ... */
+	unsigned long long *n_retry;    /* ... and how many */
+	double *arena;            /* [threads][(depth+1)*nE] */
+	LkFrame *frames;          /* [threads][depth] */
+	double *rec;              /* [threads][rec_cap*(11+nE)] scratch strips */
+	LkFrame *big_frames;      /* pool of full-size workspaces for the photons that outgrow the small ones (first launch) */
+	double *big_arena, *big_rec;
+	unsigned long long *big_next, big_n;
 	/* dense per-id outputs */
 	int8_t *status;
 	int *irefl;
@@ -767,15 +816,21 @@ __global__ void __launch_bounds__(LK_THREADS) pcb_leak_kernel(const LkParams P)
 	const LkCtx &c = P.c;
 	const int nE = c.nE;
 	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	double *arena = P.arena + tid * (unsigned long long)(LK_DEPTH + 1) * nE;
-	LkFrame *frames = P.frames + tid * (unsigned long long)LK_DEPTH;
+	double *const arena0 = P.arena + tid * (unsigned long long)(P.depth + 1) * nE;
+	LkFrame *const frames0 = P.frames + tid * (unsigned long long)P.depth;
+	double *const rec0 = P.rec + tid * (unsigned long long)P.rec_cap * (11 + nE);
 	LkOut out;
-	out.rec = P.rec + tid * (unsigned long long)LK_REC_CAP * (11 + nE);
-	unsigned long long refl_events = 0;
+	out.big_frames = P.big_frames; out.big_arena = P.big_arena; out.big_rec = P.big_rec; out.big_next = P.big_next; out.big_n = P.big_n;
+	unsigned long long refl_events = 0, wall_steps = 0;
 	for (;;) {
 		unsigned long long i = atomicAdd(P.next, 1ULL);
-		if (i >= P.n)
+		if (P.todo) {
+			if (i >= P.n_todo)
+				break;
+			i = P.todo[i];
+		} else if (i >= P.n) {
 			break;
+		}
 		StartState s0;
 		if (P.mode == 0) {
 			source_sample(P.s, c.mono, P.id0 + i, s0);
@@ -788,10 +843,25 @@ __global__ void __launch_bounds__(LK_THREADS) pcb_leak_kernel(const LkParams P)
 		}
 		out.nrec = 0;
 		out.err = 0;
+		out.rec = rec0; /* every photon starts in the thread's own (small) workspace */
+		out.cap = P.rec_cap;
+		out.depth = P.depth;
+		double *arena = arena0;
+		LkFrame *frames = frames0;
 		LkResult r;
-		lk_photon(c, s0.coords, s0.dir, s0.ev, 0.0, frames, arena, out, r, refl_events);
-		if (out.err)
+		unsigned long long ev_photon = 0, steps_photon = 0;
+		lk_photon(c, s0.coords, s0.dir, s0.ev, 0.0, frames, arena, out, r, ev_photon, steps_photon);
+		if (out.err) {
+			if (P.retry) { /* did not fit the small per-thread capacities: the second launch redoes this id with the full ones */
+				P.retry[atomicAdd(P.n_retry, 1ULL)] = i;
+				P.leak_n[i] = 0;
+				P.leak_off[i] = 0;
+				continue;
+			}
 			atomicOr(P.err, out.err);
+		}
+		refl_events += ev_photon;
+		wall_steps += steps_photon;
 		int status = r.ret;
 		const double zt = c.z[c.nmax];
 		if (P.mode == 0 && r.ret == 1) { /* exit-window test, source.c:762-777 */
@@ -850,13 +920,14 @@ __global__ void __launch_bounds__(LK_THREADS) pcb_leak_kernel(const LkParams P)
 				for (size_t k = 0; k < (size_t)keep * stride; k++)
 					P.leak_pool[off * stride + k] = out.rec[k];
 			} else {
-				atomicOr(P.err, LK_ERR_RECORDS);
+				atomicOr(P.err, LK_ERR_POOL);
 			}
 		} else {
 			P.leak_off[i] = 0;
 		}
 	}
 	atomicAdd(P.refl_events, refl_events);
+	atomicAdd(P.refl_events + 1, wall_steps);
 }
 
 /* single-item kernels for the reference's private test entry points */
@@ -865,7 +936,8 @@ __global__ void lk_unit_trace_wall_kernel(LkCtx c, const double *in, double *out
 	V3 ec = {in[0], in[1], in[2]}, ed = {in[3], in[4], in[5]};
 	double d_travel;
 	int r_cntr, q_cntr;
-	outi[0] = lk_trace_wall(c, ec, ed, d_travel, r_cntr, q_cntr);
+	unsigned long long steps = 0;
+	outi[0] = lk_trace_wall(c, ec, ed, d_travel, r_cntr, q_cntr, steps);
 	outi[1] = r_cntr;
 	outi[2] = q_cntr;
 	outd[0] = d_travel;
@@ -908,7 +980,7 @@ struct DevMem {
 /* shared driver: runs n photons (ids or replay states), fills host outputs */
 extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src, uint64_t seed, int64_t id0, int64_t n, const double *coords,
 			    const double *dir, const double *ev, int8_t *status, int *irefl, double *fields /* [F][n] field-major */, double *weights,
-			    int *leak_n, double **leak_rec, int64_t *n_leak_rec, int64_t *refl_events)
+			    int *leak_n, double **leak_rec, int64_t *n_leak_rec, int64_t *work /* [2]: capil_reflect events, wall-march steps */)
 {
 	const int nE = o->nE;
 	const int mode = src ? 0 : 1;
@@ -930,42 +1002,79 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	P.mode = mode;
 	P.id0 = (unsigned long long)id0;
 	P.n = (unsigned long long)n;
-	/* per-thread workspace: frame stack, weight arena, record strip; the thread count follows from a memory budget */
-	const size_t per_thread = (size_t)LK_DEPTH * sizeof(LkFrame) + (size_t)(LK_DEPTH + 1) * nE * 8 + (size_t)LK_REC_CAP * (11 + (size_t)nE) * 8;
+	/* Per-thread workspace: frame stack, weight arena, record strip; the thread count follows from a memory budget.  Few photons
+	 * nest deeper than a few dozen secondaries, but one that does needs LK_DEPTH frames and LK_REC_CAP records, i.e. megabytes per
+	 * thread at long energy grids -- so the first launch gives every thread small capacities (many threads), collects the ids that
+	 * did not fit, and a second launch redoes only those with the full capacities (few threads). */
+	const size_t stride = 11 + (size_t)nE;
+	auto per_thread_bytes = [&](int depth, int rcap) { return (size_t)depth * sizeof(LkFrame) + (size_t)(depth + 1) * nE * 8 + (size_t)rcap * stride * 8; };
+	const int depth1 = getenv("POLYCAP_B200_LEAK_DEPTH1") ? atoi(getenv("POLYCAP_B200_LEAK_DEPTH1")) : 48;
+	const int rcap1 = 4 * depth1;
 	size_t free_b = 0, total_b = 0;
 	LCK(cudaMemGetInfo(&free_b, &total_b));
 	size_t budget = free_b / 3;
 	if (budget > ((size_t)24 << 30))
 		budget = (size_t)24 << 30;
-	int blocks = (int)((n + LK_THREADS - 1) / LK_THREADS);
-	int max_blocks = (int)(budget / (per_thread * LK_THREADS));
-	if (max_blocks > o->sm_count * 4)
-		max_blocks = o->sm_count * 4;
-	if (max_blocks < 1)
-		max_blocks = 1;
-	if (blocks > max_blocks)
-		blocks = max_blocks;
-	const size_t threads = (size_t)blocks * LK_THREADS;
-	const size_t stride = 11 + (size_t)nE;
+	auto blocks_for = [&](int64_t items, int depth, int rcap) {
+		int blocks = (int)((items + LK_THREADS - 1) / LK_THREADS);
+		int max_blocks = (int)(budget / (per_thread_bytes(depth, rcap) * LK_THREADS));
+		if (max_blocks > o->sm_count * 4)
+			max_blocks = o->sm_count * 4;
+		if (max_blocks < 1)
+			max_blocks = 1;
+		return blocks > max_blocks ? max_blocks : blocks;
+	};
+	int blocks = blocks_for(n, depth1, rcap1);
+	size_t threads = (size_t)blocks * LK_THREADS;
 	double *d_rin = nullptr;
+	P.depth = depth1;
+	P.rec_cap = rcap1;
 	LCK(M.alloc(&P.next, 8));
-	LCK(M.alloc(&P.arena, threads * (LK_DEPTH + 1) * nE * 8));
-	LCK(M.alloc(&P.frames, threads * LK_DEPTH * sizeof(LkFrame)));
-	LCK(M.alloc(&P.rec, threads * LK_REC_CAP * stride * 8));
+	LCK(M.alloc(&P.retry, (size_t)n * 8));
+	LCK(M.alloc(&P.n_retry, 8));
+	LCK(cudaMemset(P.n_retry, 0, 8));
+	LCK(M.alloc(&P.arena, threads * (size_t)(depth1 + 1) * nE * 8));
+	LCK(M.alloc(&P.frames, threads * (size_t)depth1 * sizeof(LkFrame)));
+	LCK(M.alloc(&P.rec, threads * (size_t)rcap1 * stride * 8));
+	{ /* full-size workspaces for the deep photons of this launch: a quarter of what is left, at most 16 GB, at most one per id */
+		size_t fb = 0, tb = 0;
+		LCK(cudaMemGetInfo(&fb, &tb));
+		size_t big_budget = fb / 4;
+		if (big_budget > ((size_t)16 << 30))
+			big_budget = (size_t)16 << 30;
+		unsigned long long nb = big_budget / per_thread_bytes(LK_DEPTH, LK_REC_CAP);
+		if (nb > (unsigned long long)n)
+			nb = (unsigned long long)n;
+		if (nb > 4096)
+			nb = 4096;
+		P.big_n = nb;
+		LCK(M.alloc(&P.big_next, 8));
+		LCK(cudaMemset(P.big_next, 0, 8));
+		LCK(M.alloc(&P.big_frames, (size_t)nb * LK_DEPTH * sizeof(LkFrame)));
+		LCK(M.alloc(&P.big_arena, (size_t)nb * (LK_DEPTH + 1) * nE * 8));
+		LCK(M.alloc(&P.big_rec, (size_t)nb * LK_REC_CAP * stride * 8));
+	}
 	LCK(M.alloc(&P.status, (size_t)n));
 	LCK(M.alloc(&P.irefl, (size_t)n * 4));
 	LCK(M.alloc(&P.fields, (size_t)n * nfields * 8));
 	LCK(M.alloc(&P.weights, (size_t)n * nE * 8));
 	LCK(M.alloc(&P.leak_n, (size_t)n * 4));
 	LCK(M.alloc(&P.leak_off, (size_t)n * 8));
+	/* record pool of the wave: 24 leaks per id on average, within a third of the free memory; a wave that overflows it is
+	 * reported with return code -2 and retried by the caller with fewer ids (the reference simply reallocs per photon) */
 	P.leak_pool_cap = (unsigned long long)n * 24 + 65536;
+	{
+		const unsigned long long fit = (unsigned long long)(free_b / 3) / (stride * 8);
+		if (P.leak_pool_cap > fit)
+			P.leak_pool_cap = fit > 4096 ? fit : 4096;
+	}
 	LCK(M.alloc(&P.leak_pool, (size_t)P.leak_pool_cap * stride * 8));
 	LCK(M.alloc(&P.leak_pool_used, 8));
-	LCK(M.alloc(&P.refl_events, 8));
+	LCK(M.alloc(&P.refl_events, 16));
 	LCK(M.alloc(&P.err, 4));
 	LCK(cudaMemset(P.next, 0, 8));
 	LCK(cudaMemset(P.leak_pool_used, 0, 8));
-	LCK(cudaMemset(P.refl_events, 0, 8));
+	LCK(cudaMemset(P.refl_events, 0, 16));
 	LCK(cudaMemset(P.err, 0, 4));
 	if (mode == 1) {
 		LCK(M.alloc(&d_rin, (size_t)n * 9 * 8));
@@ -977,17 +1086,53 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	pcb_leak_kernel<<<blocks, LK_THREADS>>>(P);
 	LCK(cudaGetLastError());
 	LCK(cudaDeviceSynchronize());
+	unsigned long long n_retry = 0;
+	LCK(cudaMemcpy(&n_retry, P.n_retry, 8, cudaMemcpyDeviceToHost));
+	if (n_retry > 0) { /* second launch: the deep photons with the full capacities */
+		DevMem M2;
+		LkParams Q = P;
+		Q.depth = LK_DEPTH;
+		Q.rec_cap = LK_REC_CAP;
+		Q.todo = P.retry;
+		Q.n_todo = n_retry;
+		Q.retry = nullptr;
+		Q.n_retry = nullptr;
+		Q.big_next = nullptr;
+		Q.big_n = 0;
+		const int blocks2 = blocks_for((int64_t)n_retry, LK_DEPTH, LK_REC_CAP);
+		const size_t threads2 = (size_t)blocks2 * LK_THREADS;
+		LCK(M2.alloc(&Q.arena, threads2 * (size_t)(LK_DEPTH + 1) * nE * 8));
+		LCK(M2.alloc(&Q.frames, threads2 * (size_t)LK_DEPTH * sizeof(LkFrame)));
+		LCK(M2.alloc(&Q.rec, threads2 * (size_t)LK_REC_CAP * stride * 8));
+		LCK(cudaMemset(Q.next, 0, 8));
+		pcb_leak_kernel<<<blocks2, LK_THREADS>>>(Q);
+		LCK(cudaGetLastError());
+		LCK(cudaDeviceSynchronize());
+	}
+	if (getenv("POLYCAP_B200_PHASES"))
+	{
+		unsigned long long moved = 0;
+		cudaMemcpy(&moved, P.big_next, 8, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "polycap-b200 phases: leak wave of %lld ids: %d x %d threads with %d frames each, %llu photons moved to a full-size workspace (%llu available), "
+				"%llu ids redone in a second launch\n", (long long)n, blocks, LK_THREADS, depth1, moved, P.big_n, n_retry);
+	}
 	int err = 0;
-	unsigned long long used = 0, refl = 0;
+	unsigned long long used = 0, refl[2] = {0, 0};
 	LCK(cudaMemcpy(&err, P.err, 4, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(&used, P.leak_pool_used, 8, cudaMemcpyDeviceToHost));
-	LCK(cudaMemcpy(&refl, P.refl_events, 8, cudaMemcpyDeviceToHost));
-	if (err) {
-		g_lk_err = (err & LK_ERR_DEPTH) ? "leak transport: more than 1400 nested secondary photons" : "leak transport: leak-record capacity exceeded";
+	LCK(cudaMemcpy(refl, P.refl_events, 16, cudaMemcpyDeviceToHost));
+	if (err & (LK_ERR_DEPTH | LK_ERR_RECORDS)) {
+		g_lk_err = (err & LK_ERR_DEPTH) ? "leak transport: more than 1400 nested secondary photons" : "leak transport: more than 2048 leak records from one photon";
 		return -1;
 	}
-	if (refl_events)
-		*refl_events = (int64_t)refl;
+	if (err & LK_ERR_POOL) {
+		g_lk_err = "leak transport: the wave's leak-record pool is full (retry with fewer photon ids per wave)";
+		return -2;
+	}
+	if (work) {
+		work[0] = (int64_t)refl[0];
+		work[1] = (int64_t)refl[1];
+	}
 	LCK(cudaMemcpy(status, P.status, (size_t)n, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(irefl, P.irefl, (size_t)n * 4, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(fields, P.fields, (size_t)n * nfields * 8, cudaMemcpyDeviceToHost));

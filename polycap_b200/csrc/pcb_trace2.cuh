@@ -53,6 +53,14 @@
 #ifndef T2_EU
 #define T2_EU 2 /* deferred weights: energies per lane and pass in the energy task (independent FP64 chains per lane) */
 #endif
+#ifndef T2_EK
+#define T2_EK 1 /* deferred weights: reflections per trip of the energy task's inner loop (independent Fresnel terms to overlap) */
+#endif
+#ifndef T2_SCAN_AFTER
+#define T2_SCAN_AFTER 24 /* segment steps a photon takes inside the task that launched or reflected it before it goes to the scan queue */
+#endif
+#define T2_PRAGMA_(x) _Pragma(#x)
+#define T2_PRAGMA(x) T2_PRAGMA_(x)
 #ifndef T2_BACKOFF_MAX
 #define T2_BACKOFF_MAX 4096u /* longest sleep of a warp that finds every queue empty [ns] */
 #endif
@@ -90,6 +98,75 @@ __device__ __forceinline__ void t2_push(volatile unsigned short *buf, unsigned *
 	while (buf[t] != T2_EMPTY) {
 	}
 	buf[t] = (unsigned short)slot;
+}
+
+
+/* Energy task of the deferred-weights tracer, one pass: the lane's U energies through all nh buffered reflections of one photon
+ * (history H, 4 doubles per reflection, one entry per lane, broadcast by shuffle).  Updates w[], returns in `lead` the number of
+ * leading reflections after which one of the lane's weights was still >= 1e-4 and in `first_bad` the first reflection with a
+ * reflectivity outside [0, 1].  EXACT = false screens both tests on the high words of r and w and leaves u == 0 to chance: it
+ * returns true (for the whole warp) when any lane met a value the screens cannot decide, and the caller repeats the pass with
+ * EXACT = true.  Cost model of the inner loop (ncu, B200): an FP64 instruction holds the issue port for two cycles, any other
+ * instruction for one, so the loop is written to minimise 2 F + O. */
+template <int U, bool EXACT>
+__device__ __forceinline__ bool t2_energy_pass(const double *H, int nh, int lane, bool rough, double sig_rough, const double (&c_nre)[U], const double (&c_nim)[U],
+					       const double (&c_nsum)[U], const double (&c_i2re)[U], const double (&c_i2im)[U], const double (&c_kr)[U],
+					       double (&w)[U], int &lead, int &first_bad)
+{
+	bool still = true, sus = false;
+	_Pragma("unroll 1") for (int h0 = 0; h0 < nh; h0 += 32) {
+		double h_ct = 0, h_s2 = 0, h_fs = 0, h_al = 0; /* entry h0 + lane */
+		if (h0 + lane < nh) {
+			const double2 *hp = reinterpret_cast<const double2 *>(H + (h0 + lane) * 4);
+			const double2 a = hp[0], c = hp[1];
+			h_ct = a.x; h_s2 = a.y; h_fs = c.x; h_al = c.y;
+		}
+		const int kn = (nh - h0) < 32 ? (nh - h0) : 32;
+		T2_PRAGMA(unroll T2_EK) for (int k = 0; k < kn; k++) {
+#ifdef T2_HIST_LDG /* tuning variant: every lane reads the entry itself (one broadcast transaction per 16 bytes) instead of 6-8 shuffles */
+			const double2 *hq = reinterpret_cast<const double2 *>(H + (h0 + k) * 4);
+			const double2 ha = hq[0], hb = hq[1];
+			const double ct = ha.x, s2 = ha.y, fs = hb.x, al = hb.y;
+			(void)h_ct; (void)h_s2; (void)h_fs; (void)h_al;
+#else
+			const double ct = __shfl_sync(0xffffffffu, h_ct, k), s2 = __shfl_sync(0xffffffffu, h_s2, k);
+			const double fs = __shfl_sync(0xffffffffu, h_fs, k);
+			double al = 0;
+			if (rough)
+				al = __shfl_sync(0xffffffffu, h_al, k);
+#endif
+			bool alive_k = false, bad_k = false;
+			uint32_t hr = 0, hw = 0; /* largest high words of the lane's reflectivities / weights at this reflection */
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const double r = fresnel_rtot_fast_ns<EXACT>(c_nre[u], c_nim[u], c_nsum[u], c_i2re[u], c_i2im[u], ct, s2, fs);
+				if (rough) {
+					const double cr = c_kr[u] * al * sig_rough;
+					w[u] = w[u] * r * exp(-1. * cr * cr);
+				} else {
+					w[u] = w[u] * r; /* "* 1.0" of the reference is exact */
+				}
+				if (EXACT) {
+					bad_k |= pcb_refl_out_of_range(r);
+					alive_k |= pcb_weight_alive(w[u]);
+				} else {
+					const uint32_t a = pcb_hi_word(r), b = pcb_hi_word(w[u]);
+					hr = a > hr ? a : hr;
+					hw = b > hw ? b : hw;
+				}
+			}
+			if (!EXACT) {
+				const int sc = pcb_weight_screen_hi(hw); /* the largest weight decides "any weight >= 1e-4" unless it sits on the edge */
+				alive_k = sc > 0;
+				sus |= pcb_refl_suspect_hi(hr) | (sc < 0);
+			}
+			if (bad_k && h0 + k < first_bad)
+				first_bad = h0 + k;
+			still = still && alive_k;
+			lead += still ? 1 : 0;
+		}
+	}
+	return EXACT ? false : __any_sync(0xffffffffu, sus);
 }
 
 template <int MODE, int EXACT_W, int DEFER>
@@ -762,7 +839,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 					if (next == TQ_SCAN) {
 						S.ntrace[slot] = ntrace;
 						SD(D_LHZ) = lhz;
-						T2_SCAN_STEPS(24);
+						T2_SCAN_STEPS(T2_SCAN_AFTER);
 					}
 				} else {
 					code = 0;
@@ -898,41 +975,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 						 * where the last energy itself is -- no per-lane validity test inside the loop */
 						w[u] = val[u] ? (winit ? wscr[eu[u]] : 1.0) : 0.0;
 					}
-					int lead = 0;
-					bool still = true;
-					_Pragma("unroll 1") for (int h0 = 0; h0 < nh; h0 += 32) {
-						double h_ct = 0, h_s2 = 0, h_fs = 0, h_al = 0; /* entry h0 + lane */
-						if (h0 + lane < nh) {
-							const double2 *hp = reinterpret_cast<const double2 *>(H + (h0 + lane) * 4);
-							const double2 a = hp[0], c = hp[1];
-							h_ct = a.x; h_s2 = a.y; h_fs = c.x; h_al = c.y;
-						}
-						const int kn = (nh - h0) < 32 ? (nh - h0) : 32;
-						_Pragma("unroll 1") for (int k = 0; k < kn; k++) {
-							const double ct = __shfl_sync(0xffffffffu, h_ct, k), s2 = __shfl_sync(0xffffffffu, h_s2, k);
-							const double fs = __shfl_sync(0xffffffffu, h_fs, k);
-							double al = 0;
-							if (rough)
-								al = __shfl_sync(0xffffffffu, h_al, k);
-							bool alive_k = false, bad_k = false;
+					/* fast pass: the survival and range tests are screened on the high words (integer pipe), u == 0 is not looked for */
+					int lead = 0, fb = 1 << 30;
+					const bool redo = t2_energy_pass<U, false>(H, nh, lane, rough, sig_rough, c_nre, c_nim, c_nsum, c_i2re, c_i2im, c_kr, w, lead, fb);
+					if (redo) { /* a value at the edge of a test, an infinity or a NaN: the same pass with the plain comparisons */
 #pragma unroll
-							for (int u = 0; u < U; u++) {
-								const double r = fresnel_rtot_fast_ns(c_nre[u], c_nim[u], c_nsum[u], c_i2re[u], c_i2im[u], ct, s2, fs);
-								if (rough) {
-									const double cr = c_kr[u] * al * sig_rough;
-									w[u] = w[u] * r * exp(-1. * cr * cr);
-								} else {
-									w[u] = w[u] * r; /* "* 1.0" of the reference is exact */
-								}
-								bad_k |= pcb_refl_out_of_range(r);
-								alive_k |= pcb_weight_alive(w[u]);
-							}
-							if (bad_k && h0 + k < first_bad)
-								first_bad = h0 + k;
-							still = still && alive_k;
-							lead += still ? 1 : 0;
-						}
+						for (int u = 0; u < U; u++)
+							w[u] = val[u] ? (winit ? wscr[eu[u]] : 1.0) : 0.0;
+						lead = 0;
+						fb = 1 << 30;
+						t2_energy_pass<U, true>(H, nh, lane, rough, sig_rough, c_nre, c_nim, c_nsum, c_i2re, c_i2im, c_kr, w, lead, fb);
 					}
+					first_bad = fb < first_bad ? fb : first_bad;
 					const int lead_w = __reduce_max_sync(0xffffffffu, lead);
 					k_dead = lead_w > k_dead ? lead_w : k_dead;
 #pragma unroll
@@ -1063,7 +1117,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 								flags |= F_DEEP;
 							T2_TRACE_BEGIN(false);
 							if (next == TQ_SCAN)
-								T2_SCAN_STEPS(24);
+								T2_SCAN_STEPS(T2_SCAN_AFTER);
 						}
 					}
 					SD(D_EX) = ex; SD(D_EY) = ey; SD(D_EZ) = ez;
@@ -1140,7 +1194,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) pcb_trace2_kernel(const PcbTrac
 		atomicAdd(&P.wc->solves, (unsigned long long)wst[W_SOLVES]);
 		atomicAdd(&P.wc->reflections, (unsigned long long)wst[W_REFL]);
 		atomicAdd(&P.wc->launched, (unsigned long long)wst[W_LAUNCH]);
-		for (int k = 0; k < 8; k++)
+		for (int k = 0; k < 5; k++) /* dbg[5] is the leak tracer's wall-step counter */
 			atomicAdd(&P.wc->dbg[k], (unsigned long long)wst[W_BATCHES + k]);
 	}
 }

@@ -107,7 +107,7 @@ extern "C" long hm_obtuse_mismatches(long n)
 		if (pcb_acos_is_obtuse(v) != (acos(v) > M_PI / 2. || acos(v) < 0.)) bad++;
 	return bad;
 }
-// pcb_refl_out_of_range / pcb_weight_alive (integer compares on the high word) against the comparisons capil_reflect writes
+// pcb_refl_out_of_range / pcb_weight_alive and their high-word screens against the comparisons capil_reflect writes
 // (capil.c:636-650): random bit patterns, the neighbourhoods of 0, 1e-4 and 1 in ulps, signed zeros, infinities, NaNs of both signs
 extern "C" long hm_predicate_mismatches(long n)
 {
@@ -115,6 +115,12 @@ extern "C" long hm_predicate_mismatches(long n)
 	auto chk = [&](double v) {
 		if (pcb_refl_out_of_range(v) != (v < 0. || v > 1.)) bad++;
 		if (pcb_weight_alive(v) != (v >= 1.e-4)) bad++;
+		/* the screens may say "undecided / suspect", never the wrong thing */
+		const uint32_t hi = pcb_hi_word(v);
+		if (!pcb_refl_suspect_hi(hi) && (v < 0. || v > 1. || v != v)) bad++;
+		const int sc = pcb_weight_screen_hi(hi);
+		if (sc == 1 && !(v >= 1.e-4)) bad++;
+		if (sc == 0 && (v >= 1.e-4)) bad++;
 	};
 	uint64_t s = 99;
 	for (long i = 0; i < n; i++) {

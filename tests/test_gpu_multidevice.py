@@ -80,3 +80,37 @@ def test_real_devices(pc, monkeypatch):
     staged = _run(pc, monkeypatch, "all", 60000, energies)
     _same(one, staged)
     assert np.array_equal(allg[0], staged[0])  # same terms in the same (device) order on both paths
+
+
+@pytest.mark.parametrize("devices", [None, "0,0,0"])
+def test_stream_chunks_equal_one_call(pc, monkeypatch, devices):
+    """polycap_b200_stream_*: the records of a run delivered in chunks (N3) are the records of one big call, in the same order,
+    and the running tallies are those of the ids consumed so far"""
+    if devices is None:
+        monkeypatch.delenv("POLYCAP_B200_DEVICES", raising=False)
+    else:
+        monkeypatch.setenv("POLYCAP_B200_DEVICES", devices)
+    energies = np.linspace(1.0, 30.0, 12)
+    src = _source(pc, energies)
+    st = pc.Stream(src, seed=90210)
+    chunks = [st.next(7000), st.next(13000), st.next(5000)]
+    ids, sw, cnt = st.totals()
+    n_tot = sum(f.shape[1] for f, _ in chunks)
+    assert n_tot == 25000 and cnt["exit"] == 25000 and cnt["ids"] == ids
+    one = _run(pc, monkeypatch, None, 25000, energies)
+    rec = one[3]
+    F = np.concatenate([f for f, _ in chunks], axis=1)
+    Wt = np.concatenate([w for _, w in chunks], axis=0)
+    assert np.array_equal(Wt, rec["exit_coord_weights"])
+    for k in range(3):
+        assert np.array_equal(F[8 + k], rec["pc_exit_coords"][k])
+    assert np.array_equal(F[15].astype(np.int64), rec["pc_exit_nrefl"]) and np.array_equal(F[16], rec["pc_exit_dtravel"])
+    started = cnt["exit"] + cnt["not_entered"] + cnt["not_transmitted"]
+    assert started == one[1]
+    assert np.allclose(sw / started, one[0], rtol=1e-12, atol=0)
+    # tally-only continuation with an id budget: no records, ids advance by exactly the budget
+    n = st.next(10**9, max_ids=50000, records=False)
+    ids2, sw2, cnt2 = st.totals()
+    assert ids2 == ids + 50000 and cnt2["exit"] == 25000 + n and np.all(sw2 >= sw)
+    sw3, cnt3, _, _ = src.run_ids(90210, 0, ids2, status=False)
+    assert cnt3["exit"] == cnt2["exit"] and np.allclose(sw3, sw2, rtol=1e-12)

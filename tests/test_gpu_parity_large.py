@@ -20,6 +20,14 @@ THREADS = os.cpu_count() or 8
 SIO2 = {8: 53.0, 14: 47.0}
 
 
+def _note(text):
+    """measured margins, kept with the GPU run's other outputs when that directory exists"""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_margins.txt"), "a") as f:
+            f.write(text + "\n")
+
+
 def _setup(pc, harness, name, energies):
     g = load_golden(name)
     prof = pc.Profile.new_from_arrays(g["ext"], g["cap"], g["z"])
@@ -52,6 +60,7 @@ def _compare(src, orc, o, seed, id0, n, chunk, min_exit):
         assert cnt["ids"] == m
         tot["exit"] += cnt["exit"]
         tot["refl_all"] += cnt["refl_all"]
+    _note("per-photon vs oracle: nE=%d ids=%d exits=%d worst record rel err %.3e, worst tally rel err %.3e" % (o.nE, n, tot["exit"], worst_rec, worst_sw))
     assert worst_rec <= RTOL, worst_rec
     assert worst_sw <= RTOL, worst_sw
     assert tot["exit"] >= min_exit, tot

@@ -190,3 +190,33 @@ def test_write_errors(pc, efficiencies):
     err = C.POINTER(Err)()
     assert not lib.polycap_transmission_efficiencies_write_hdf5(C.byref(eff), b"/hoahohfhwofh/hohadohfowf.h5", C.byref(err))
     assert err.contents.code == 2  # POLYCAP_ERROR_IO, tests/source.c:294-296
+
+
+def test_h5py_reads_the_file(pc, efficiencies, tmp_path):
+    """the writer is restated from the format specification and had only been re-read by this file's own parser.
+    Wherever a real HDF5 reader is importable (h5py; none in this image) every dataset and Units attribute is compared through it."""
+    h5py = pytest.importorskip("h5py")
+    eff, keep = efficiencies
+    lib = C.CDLL(pc.LIB_PATH)
+    lib.polycap_transmission_efficiencies_write_hdf5.restype = C.c_bool
+    lib.polycap_transmission_efficiencies_write_hdf5.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    path = str(tmp_path / "out.h5")
+    assert lib.polycap_transmission_efficiencies_write_hdf5(C.byref(eff), path.encode(), None)
+    own = H5(path)
+
+    def walk(group_addr, prefix, out):
+        for name, (oh, _) in own.group(group_addr).items():
+            try:
+                out[prefix + name] = own.dataset(oh)
+            except Exception:
+                walk(oh, prefix + name + "/", out)
+    mine = {}
+    walk(own.root[0], "/", mine)
+    assert len(mine) > 20
+    with h5py.File(path, "r") as f:
+        for name, (data, attrs) in mine.items():
+            ds = f[name]
+            assert np.array_equal(np.asarray(ds, dtype=np.float64).reshape(data.shape), data), name
+            for k, v in attrs.items():
+                got = ds.attrs[k]
+                assert (got.decode() if isinstance(got, bytes) else str(got)) == v, (name, k)

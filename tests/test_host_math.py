@@ -164,8 +164,9 @@ def test_segment_matches_oracle_bitwise(hm, harness, orc):
     assert hits > 300
 
 
-def test_integer_compare_predicates_equal_the_float_comparisons(hm):
-    """pcb_refl_out_of_range(r) == (r < 0 || r > 1) and pcb_weight_alive(w) == (w >= 1e-4) for every bit pattern class"""
+def test_high_word_screens_never_contradict_the_float_comparisons(hm):
+    """the high-word screens of the energy loop (pcb_refl_suspect_hi, pcb_weight_screen_hi) either agree with r < 0 || r > 1 and
+    w >= 1e-4 or say "undecided", for every bit pattern class"""
     hm.hm_predicate_mismatches.restype = C.c_long
     hm.hm_predicate_mismatches.argtypes = [C.c_long]
     assert hm.hm_predicate_mismatches(2_000_000) == 0
