@@ -1354,6 +1354,63 @@ static void append_leaks(polycap_photon *photon, size_t nE, const double *lrec, 
 	}
 }
 
+/* polycap_capil_reflect / polycap_capil_trace with leak_calc = true: one step of the leak state machine of pcb_leak.cu on the
+ * caller's photon (capil.c:565-891, 1197-1361).  mode 1: reflect on `normal`; mode 2: trace (cap_x / cap_y give the capillary axis). */
+static int leak_unit_step(polycap_photon *photon, polycap_description *d, int mode, polycap_vector3 normal, int *ix, const double *cap_x, const double *cap_y,
+			  polycap_error **error, const char *W)
+{
+	const polycap_profile *p = d->profile;
+	const size_t nE = photon->n_energies;
+	double A = 0, B = 0;
+	if (mode == 2) { /* the axis arrays must describe a capillary of the hexagonal lattice: cap_x[i] = A hexz[i], cap_y[i] = B hexz[i] */
+		const double n_shells = round(sqrt(12. * d->n_cap - 3.) / 6. - 0.5);
+		const double den = 2. * 0.86602540378443864676 * (n_shells + 1);
+		int k = -1;
+		for (int i = 0; i <= p->nmax && k < 0; i++)
+			if (p->ext[i] != 0.)
+				k = i;
+		if (k >= 0) {
+			A = cap_x[k] / (p->ext[k] / den);
+			B = cap_y[k] / (p->ext[k] / den);
+		}
+		for (int i = 0; i <= p->nmax; i++) {
+			const double hz = p->ext[i] / den;
+			if (fabs(A * hz - cap_x[i]) > 1e-12 * (fabs(cap_x[i]) + 1e-300) + 1e-300 || fabs(B * hz - cap_y[i]) > 1e-12 * (fabs(cap_y[i]) + 1e-300) + 1e-300) {
+				polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc=true needs cap_x / cap_y that follow the external profile (a capillary of the lattice)", W);
+				return -1;
+			}
+		}
+	}
+	pcb_gpu_optic *g = optic_for(d, nE, photon->energies, photon->amu, photon->scatf, -1, error, W);
+	if (!g)
+		return -1;
+	const double in[16] = {photon->exit_coords.x, photon->exit_coords.y, photon->exit_coords.z, photon->exit_direction.x, photon->exit_direction.y,
+			       photon->exit_direction.z, photon->exit_electric_vector.x, photon->exit_electric_vector.y, photon->exit_electric_vector.z,
+			       normal.x, normal.y, normal.z, (double)photon->i_refl, photon->d_travel, A, B};
+	double outs[13];
+	double *lrec = NULL;
+	int64_t n_lrec = 0;
+	if (pcb_gpu_leak_unit_step(g, mode, in, ix ? *ix : 0, photon->weight, outs, &lrec, &n_lrec)) {
+		gpu_fail(error, W);
+		return -1;
+	}
+	const int rc = (int)outs[0];
+	if (n_lrec > 0)
+		append_leaks(photon, nE, lrec, n_lrec);
+	free(lrec);
+	photon->exit_direction.x = outs[4]; photon->exit_direction.y = outs[5]; photon->exit_direction.z = outs[6];
+	if (mode == 2) {
+		photon->exit_coords.x = outs[1]; photon->exit_coords.y = outs[2]; photon->exit_coords.z = outs[3];
+		photon->d_travel = outs[11];
+		photon->i_refl = (int64_t)outs[10];
+		*ix = (int)outs[12];
+	}
+	if (mode == 2 || rc == 0 || rc == 1 || rc == -2) {
+		photon->exit_electric_vector.x = outs[7]; photon->exit_electric_vector.y = outs[8]; photon->exit_electric_vector.z = outs[9];
+	}
+	return rc;
+}
+
 extern "C" int polycap_capil_reflect(polycap_photon *photon, polycap_vector3 surface_norm, bool leak_calc, polycap_error **error) /* capil.c:565-891 */
 {
 	static const char *W = "polycap_capil_reflect";
@@ -1373,9 +1430,11 @@ extern "C" int polycap_capil_reflect(polycap_photon *photon, polycap_vector3 sur
 	energy_constants_for(photon, d, ec);
 	double out[6];
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
-	if (leak_calc) { /* the leak state machine runs whole photons (pcb_leak.cu); its single-step form is not exposed */
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc=true is served by polycap_photon_launch / polycap_source_get_transmission_efficiencies", W);
-		return -1;
+	if (leak_calc) {
+		int rc = leak_unit_step(photon, d, 1, surface_norm, NULL, NULL, NULL, error, W);
+		if (rc == -1 && error && *error == NULL) /* capil.c:599-602: the one error a reflect reports itself */
+			polycap_set_error(error, POLYCAP_ERROR_INVALID_ARGUMENT, "%s: alfa must be greater than 0", W);
+		return rc;
 	}
 	const double in[9] = {photon->exit_direction.x, photon->exit_direction.y, photon->exit_direction.z, photon->exit_electric_vector.x,
 			      photon->exit_electric_vector.y, photon->exit_electric_vector.z, surface_norm.x, surface_norm.y, surface_norm.z};
@@ -1418,8 +1477,9 @@ extern "C" int polycap_capil_trace(int *ix, polycap_photon *photon, polycap_desc
 	long long irefl = photon->i_refl;
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
 	if (leak_calc) {
-		polycap_set_error(error, POLYCAP_ERROR_UNSUPPORTED, "%s: leak_calc=true is served by polycap_photon_launch / polycap_source_get_transmission_efficiencies", W);
-		return -1;
+		polycap_vector3 none = {0., 0., 0.};
+		polycap_norm(&photon->start_direction); /* capil.c:1237 */
+		return leak_unit_step(photon, description, 2, none, ix, cap_x, cap_y, error, W);
 	}
 	int rc = pcb_unit_trace(in, ix, &irefl, p->z, p->cap, p->ext, cap_x, cap_y, p->nmax, n_shells == 0., ec.data(), (int)photon->n_energies,
 				description->sig_rough, photon->weight, out);

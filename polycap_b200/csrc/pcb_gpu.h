@@ -116,6 +116,9 @@ int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *coords, const
 int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s, uint64_t seed, int64_t id0, int64_t n_ids, int64_t n_wanted, double *d_sum_weights,
 			  int64_t *d_counters, double *d_rec_fields, double *d_rec_weights, int64_t rec_cap, int64_t rec_base, int64_t *ids_used,
 			  int64_t *n_exit, double **leak_rec, int64_t *n_leak_rec);
+/* one polycap_capil_reflect (mode 1) / polycap_capil_trace (mode 2) with leak_calc = true; arguments as pcb_leak_unit_step (pcb_leak.h) */
+int pcb_gpu_leak_unit_step(pcb_gpu_optic *g, int mode, const double in[16], int ix, double *weights, double outs[13], double **leak_rec,
+			   int64_t *n_leak_rec);
 int pcb_gpu_leak_trace_wall(pcb_gpu_optic *g, const double in[6], double *d_travel, int *r_cntr, int *q_cntr);
 
 /* dense per-id view of the last wave (debug / parity): status[n] and the 17+nE record of every id */

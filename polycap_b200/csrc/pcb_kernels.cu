@@ -1220,6 +1220,19 @@ extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s,
 	return 0;
 }
 
+extern "C" int pcb_gpu_leak_unit_step(pcb_gpu_optic *g, int mode, const double in[16], int ix, double *weights, double outs[13], double **leak_rec,
+				      int64_t *n_leak_rec)
+{
+	CK(cudaSetDevice(g->device));
+	pcb_leak_optic v;
+	leak_view(g, &v);
+	g->n_kernels++;
+	int rc = pcb_leak_unit_step(&v, mode, in, ix, weights, outs, leak_rec, n_leak_rec);
+	if (rc)
+		g_last_error = pcb_leak_last_error();
+	return rc;
+}
+
 extern "C" int pcb_gpu_leak_trace_wall(pcb_gpu_optic *g, const double in[6], double *d_travel, int *r_cntr, int *q_cntr)
 {
 	CK(cudaSetDevice(g->device));

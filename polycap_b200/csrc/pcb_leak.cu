@@ -58,7 +58,7 @@ struct LkFrame {
 	double *w;
 };
 
-enum { CONT_TRACE = 0, CONT_FACE = 1 };
+enum { CONT_TRACE = 0, CONT_FACE = 1, CONT_UNIT = 2 };
 
 struct LkOut {
 	double *rec;    /* this thread's strip: cap x (11+nE) */
@@ -457,17 +457,31 @@ struct LkResult {
 
 /* polycap_photon_launch with leak_calc = true (photon.c:390-955), iterative over an explicit frame stack.
  * `arena` holds (out.depth+1) weight vectors of nE doubles; arena[0..nE) ends up with the primary's weights. */
+/* Single-step use of the state machine (the reference's TEST_BUILD entry points with leak_calc = true): the photon state comes from
+ * the caller instead of the launch preamble, and the machine stops when the primary frame has finished
+ *   mode 1  one polycap_capil_reflect (capil.c:565-891) on wall normal `normal`: ret = 1 / 0 / -1 / -2
+ *   mode 2  one polycap_capil_trace (capil.c:1197-1361):                        ret = 1 / 0 / -1 / -2 / -3 */
+struct LkUnit {
+	int mode;
+	V3 normal;
+	long long irefl;
+	double A, B;
+	int ix;
+};
+
 __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, double d_travel0, LkFrame *&fr, double *&arena, LkOut &out, LkResult &res,
-			  unsigned long long &n_refl_events, unsigned long long &n_wall_steps)
+			  unsigned long long &n_refl_events, unsigned long long &n_wall_steps, const LkUnit *unit = nullptr)
 {
 	const int nm = c.nmax, nE = c.nE;
 	int sp = 0;
 	LkFrame *f = &fr[0];
 	f->w = arena;
-	for (int e = 0; e < nE; e++)
-		f->w[e] = 1.;
-	f->irefl = 0;
+	if (!unit) /* single-step entries arrive with the photon's weights in arena[0, nE) */
+		for (int e = 0; e < nE; e++)
+			f->w[e] = 1.;
+	f->irefl = unit ? unit->irefl : 0;
 	f->dtrav = d_travel0;
+	const V3 raw_dir = sd;
 	norm3(sd);
 	const V3 start_dir = sd;
 	f->ec = sc;
@@ -502,7 +516,25 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 	enum { S_TRACE_LOOP, S_REFLECT, S_AFTER_REFLECT, S_FRAME_DONE, S_FINISH };
 	int state = S_FINISH, esc = 0, riesc = 0;
 	V3 refl_normal = {0, 0, 1};
-	if (!finished) {
+	int unit_ret = -1;
+	if (unit) { /* the caller's photon as it is: no launch preamble */
+		finished = true; /* keeps the launch epilogue out */
+		f->ed = raw_dir; /* capil_reflect / capil_trace normalise it themselves, once */
+		f->A = unit->A;
+		f->B = unit->B;
+		f->ix = unit->ix;
+		f->it = 0;
+		f->it_end = nm;
+		f->sn = unit->normal;
+		f->cosalfa = 0;
+		if (unit->mode == 1) {
+			f->cont = CONT_UNIT;
+			refl_normal = unit->normal;
+			state = S_REFLECT;
+		} else {
+			state = S_TRACE_LOOP;
+		}
+	} else if (!finished) {
 		f->A = (2. * q_i + r_i) * PCB_COSPI_6;
 		f->B = r_i * (3. / 2);
 		f->ix = lk_z_index_incl(c, sc.z);
@@ -692,6 +724,7 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 			state = S_AFTER_REFLECT;
 		} else if (state == S_FRAME_DONE) {
 			if (sp == 0) {
+				unit_ret = esc; /* single polycap_capil_trace that found no reflection: -1 / -2 / -3 */
 				state = S_FINISH;
 				continue;
 			}
@@ -719,6 +752,11 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 				state = S_FINISH;
 				continue;
 			}
+			if (f->cont == CONT_UNIT) { /* single polycap_capil_reflect: its return value is the result */
+				unit_ret = riesc;
+				state = S_FINISH;
+				continue;
+			}
 			if (riesc == 1) { /* capil.c:1346-1352 */
 				f->ed.x = f->ed.x - 2.0 * f->cosalfa * f->sn.x;
 				f->ed.y = f->ed.y - 2.0 * f->cosalfa * f->sn.y;
@@ -733,6 +771,10 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 			}
 			f->last_esc = esc;
 			state = (esc == 1) ? S_TRACE_LOOP : S_FRAME_DONE;
+			if (unit && sp == 0) { /* single polycap_capil_trace: one wall hit of the primary, reflected */
+				unit_ret = esc;
+				state = S_FINISH;
+			}
 		}
 	}
 
@@ -769,6 +811,8 @@ __device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, do
 			norm3(f->ed);
 		}
 	}
+	if (unit)
+		ret = unit_ret;
 	res.ret = ret;
 	res.ec = f->ec;
 	res.ed = f->ed;
@@ -941,6 +985,41 @@ __global__ void lk_unit_trace_wall_kernel(LkCtx c, const double *in, double *out
 	outi[1] = r_cntr;
 	outi[2] = q_cntr;
 	outd[0] = d_travel;
+}
+
+/* single polycap_capil_reflect / polycap_capil_trace with leak_calc = true on one photon state:
+ * in[16] = coords(3) direction(3) elecv(3) normal(3) i_refl d_travel A B; ix; w[nE] in/out; outs[13] = ret coords(3) direction(3) elecv(3) i_refl d_travel ix */
+__global__ void lk_unit_step_kernel(LkCtx c, int mode, const double *in, int ix, double *w, LkFrame *frames, double *arena, double *rec, int rec_cap, int depth,
+				    double *outs, int *nrec_out, int *err_out)
+{
+	LkOut out;
+	out.rec = rec; out.nrec = 0; out.err = 0; out.cap = rec_cap; out.depth = depth;
+	out.big_frames = nullptr; out.big_arena = nullptr; out.big_rec = nullptr; out.big_next = nullptr; out.big_n = 0;
+	for (int e = 0; e < c.nE; e++)
+		arena[e] = w[e];
+	LkUnit u;
+	u.mode = mode;
+	u.normal.x = in[9]; u.normal.y = in[10]; u.normal.z = in[11];
+	u.irefl = (long long)in[12];
+	u.A = in[14]; u.B = in[15];
+	u.ix = ix;
+	V3 sc = {in[0], in[1], in[2]}, sd = {in[3], in[4], in[5]}, sev = {in[6], in[7], in[8]};
+	LkResult r;
+	unsigned long long ev = 0, steps = 0;
+	LkFrame *fr = frames;
+	double *ar = arena;
+	lk_photon(c, sc, sd, sev, in[13], fr, ar, out, r, ev, steps, &u);
+	for (int e = 0; e < c.nE; e++)
+		w[e] = ar[e];
+	outs[0] = (double)r.ret;
+	outs[1] = r.ec.x; outs[2] = r.ec.y; outs[3] = r.ec.z;
+	outs[4] = r.ed.x; outs[5] = r.ed.y; outs[6] = r.ed.z;
+	outs[7] = r.ev.x; outs[8] = r.ev.y; outs[9] = r.ev.z;
+	outs[10] = (double)r.irefl;
+	outs[11] = r.dtrav;
+	outs[12] = (double)fr[0].ix;
+	*nrec_out = out.nrec;
+	*err_out = out.err;
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -1153,6 +1232,47 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 		}
 	*leak_rec = recs;
 	*n_leak_rec = (int64_t)w;
+	return 0;
+}
+
+extern "C" int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const double in[16], int ix, double *weights, double outs[13], double **leak_rec,
+				  int64_t *n_leak_rec)
+{
+	LkCtx c{};
+	c.nmax = o->nmax; c.nE = o->nE; c.mono = o->mono; c.monotonic = o->monotonic; c.n_shells = o->n_shells; c.sig_rough = o->sig_rough;
+	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
+	const size_t nE = (size_t)o->nE, stride = 11 + nE;
+	*leak_rec = nullptr;
+	*n_leak_rec = 0;
+	DevMem M;
+	double *d_in, *d_w, *d_arena, *d_rec, *d_outs;
+	LkFrame *d_frames;
+	int *d_i;
+	LCK(M.alloc(&d_in, 16 * 8));
+	LCK(M.alloc(&d_w, nE * 8));
+	LCK(M.alloc(&d_arena, (size_t)(LK_DEPTH + 1) * nE * 8));
+	LCK(M.alloc(&d_frames, (size_t)LK_DEPTH * sizeof(LkFrame)));
+	LCK(M.alloc(&d_rec, (size_t)LK_REC_CAP * stride * 8));
+	LCK(M.alloc(&d_outs, 13 * 8));
+	LCK(M.alloc(&d_i, 8));
+	LCK(cudaMemcpy(d_in, in, 16 * 8, cudaMemcpyHostToDevice));
+	LCK(cudaMemcpy(d_w, weights, nE * 8, cudaMemcpyHostToDevice));
+	lk_unit_step_kernel<<<1, 1>>>(c, mode, d_in, ix, d_w, d_frames, d_arena, d_rec, LK_REC_CAP, LK_DEPTH, d_outs, d_i, d_i + 1);
+	LCK(cudaGetLastError());
+	int hi[2];
+	LCK(cudaMemcpy(hi, d_i, 8, cudaMemcpyDeviceToHost));
+	LCK(cudaMemcpy(outs, d_outs, 13 * 8, cudaMemcpyDeviceToHost));
+	LCK(cudaMemcpy(weights, d_w, nE * 8, cudaMemcpyDeviceToHost));
+	if (hi[1]) {
+		g_lk_err = (hi[1] & LK_ERR_DEPTH) ? "leak transport: more than 1400 nested secondary photons" : "leak transport: more than 2048 leak records from one photon";
+		return -1;
+	}
+	if (hi[0] > 0) {
+		double *recs = (double *)malloc((size_t)hi[0] * stride * 8);
+		LCK(cudaMemcpy(recs, d_rec, (size_t)hi[0] * stride * 8, cudaMemcpyDeviceToHost));
+		*leak_rec = recs;
+		*n_leak_rec = hi[0];
+	}
 	return 0;
 }
 

@@ -25,6 +25,13 @@ int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src, uint64_t s
 		 const double *ev, int8_t *status, int *irefl, double *fields, double *weights, int *leak_n, double **leak_rec, int64_t *n_leak_rec,
 		 int64_t *work /* [2] or NULL: capil_reflect events, wall-march steps (capil.c:1018-1068) */);
 
+/* One polycap_capil_reflect (mode 1) or polycap_capil_trace (mode 2) with leak_calc = true on one photon state:
+ * in[16] = coords(3) direction(3) elecv(3) wall normal(3) i_refl d_travel A B (capillary axis: cap_x[i] = A*hexz[i], cap_y[i] = B*hexz[i]),
+ * ix = segment index; weights[nE] in/out; outs[13] = return code, coords(3), direction(3), elecv(3), i_refl, d_travel, ix;
+ * *leak_rec = malloc'd leak records of the step (layout of pcb_leak_run).  Returns 0, or -1 with pcb_leak_last_error(). */
+int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const double in[16], int ix, double *weights, double outs[13], double **leak_rec,
+		       int64_t *n_leak_rec);
+
 /* polycap_capil_trace_wall on one photon state in[6] = coords(3), direction(3) */
 int pcb_leak_unit_trace_wall(const pcb_leak_optic *o, const double in[6], double *d_travel, int *r_cntr, int *q_cntr);
 
