@@ -458,8 +458,15 @@ def leak_record(ctx, pc, w, n_exit, cpu_seconds):
         dt = time.perf_counter() - t0
     started, exits = result_counts(te)
     n_ext, n_int = sum(1 for _ in te.extleak_data), sum(1 for _ in te.intleak_data)
+    cnt = pc.last_run_counters() or {}
+    # SURVEY 8d flop model with the leak terms: 76 instead of 70 per (reflection x energy), 60 per step of the wall march
+    flops = (F_LAUNCH * cnt.get("launched", 0) + F_REFL * cnt.get("refl_all", 0) + 76 * nE * cnt.get("refl_all", 0) + F_EXIT * exits + 60 * cnt.get("wall_steps", 0))
     out = {"workload": w["desc"] + " -- leak_calc = true", "n_energies": nE, "value": started / dt, "unit": "photons/s", "seconds": dt, "exits": exits,
-           "simulated_photons": started, "external_leak_records": n_ext, "internal_leak_records": n_int}
+           "simulated_photons": started, "external_leak_records": n_ext, "internal_leak_records": n_int,
+           "reflection_events_incl_secondaries": cnt.get("refl_all"), "wall_march_steps": cnt.get("wall_steps"),
+           "roofline": {"bound": "fp64", "achieved": flops / dt / 1e12, "peak": ctx.dfma_peak, "unit": "TFLOP/s", "frac": flops / dt / 1e12 / ctx.dfma_peak if ctx.dfma_peak else None,
+                        "model": "155*launched + 445*refl + 76*nE*refl + 100*exit + 60*wall_steps (SURVEY 8d, leak terms); segment steps of the leak tracer are not counted",
+                        "kernel": "pcb_leak_kernel (one thread per primary photon, explicit frame stack)"}}
     try:
         ref, rsrc = reference_setup(w)
         with quiet_stdout():
@@ -603,6 +610,8 @@ def main():
     # ---- the library's own multi-device path: ONE process (rank 0) shards one call over all N devices (the other ranks wait)
     one_process = None
     if world > 1 and not args.no_e2e:
+        # the idle ranks must not wait in an NCCL barrier: its kernel spins on their GPU and would time-slice with rank 0's kernels there
+        cpu_group = dist.new_group(backend="gloo")
         barrier(ctx)
         if rank == 0:
             try:
@@ -616,6 +625,7 @@ def main():
                                                   all_ranks=False)
             except Exception as exc:
                 one_process = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        dist.barrier(group=cpu_group)  # host-side wait (gloo): the other ranks' GPUs stay free for rank 0's call
         barrier(ctx)
 
     if rank == 0:

@@ -39,6 +39,7 @@ enum { LK_ERR_DEPTH = 1, LK_ERR_RECORDS = 2, LK_ERR_POOL = 4 }; /* RECORDS: one 
 
 struct LkCtx {
 	int nmax, nE, mono, monotonic;
+	int no_fast_march; /* POLYCAP_B200_LEAK_FULL_MARCH=1: every step of the wall march takes the reference's full step (checking aid) */
 	double n_shells, sig_rough;
 	const double *z, *cap, *ext, *hexz; /* global */
 	const double *ec;                   /* [EC_ROWS][nE] */
@@ -317,9 +318,47 @@ __device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_tra
 	} else {
 		double dist = 0;
 		for (;;) {
-			do { /* march in steps of a tenth of the bore radius until the hex cell changes (capil.c:1018-1068) */
+			/* March in steps of a tenth of the bore radius until the hex cell changes (capil.c:1018-1068).  A step is eventful when the point
+			 * falls back into the photon's own bore, leaves its hexagonal cell or passes the end of the optic; between the bore wall and
+			 * the cell boundary thousands of steps are none of that.  Such a step is recognised from the squared distance to the cell's
+			 * axis and the three edge normals of the hexagon (bounds taken 1e-9 inside the safe zone, rounding differences to the
+			 * reference's own expressions are ~1e-16) and then only advances the path length and the z index, exactly as the reference
+			 * does; everything else takes the reference's full step, so the outcome is the reference's step for step. */
+			const bool fast_ok = c.monotonic && ed.z >= 0. && !c.no_fast_march;
+			const double inv_den = 1.0 / (2. * PCB_COSPI_6 * (n_shells + 1));
+			const double Ai = (2. * q_i + r_i) * PCB_COSPI_6, Bi = r_i * (3. / 2);
+			int zc = -1;
+			double seg_z0 = 0, seg_e0 = 0, seg_c0 = 0, seg_se = 0, seg_sc = 0;
+			for (;;) {
 				n_steps++;
 				dist += c.cap[z_id] / 10.;
+				if (fast_ok) {
+					const double p0z = ec.z + dist * ed.z;
+					int zi = z_id;
+					if (!(c.z[zi] <= p0z))
+						zi = lk_z_index(c, p0z);
+					while (zi + 1 < nm && c.z[zi + 1] <= p0z)
+						zi++;
+					if (zi != zc) {
+						zc = zi;
+						seg_z0 = c.z[zi];
+						const double dz = c.z[zi + 1] - seg_z0;
+						seg_e0 = c.ext[zi];
+						seg_c0 = c.cap[zi];
+						seg_se = (c.ext[zi + 1] - seg_e0) / dz;
+						seg_sc = (c.cap[zi + 1] - seg_c0) / dz;
+					}
+					const double t = p0z - seg_z0;
+					const double hz = (seg_se * t + seg_e0) * inv_den;
+					const double rr = (seg_sc * t + seg_c0) * (1. + 1.e-9);
+					const double ux = (ec.x + dist * ed.x) - Ai * hz, uy = (ec.y + dist * ed.y) - Bi * hz;
+					const double h = PCB_COSPI_6 * hz * (1. - 1.e-9);
+					if (rr > 0. && hz > 0. && ux * ux + uy * uy > rr * rr && fabs(ux) < h && fabs(0.5 * ux + PCB_COSPI_6 * uy) < h &&
+					    fabs(0.5 * ux - PCB_COSPI_6 * uy) < h && p0z <= c.z[nm]) {
+						z_id = zi;
+						continue;
+					}
+				}
 				p0.x = ec.x + dist * ed.x;
 				p0.y = ec.y + dist * ed.y;
 				p0.z = ec.z + dist * ed.z;
@@ -348,7 +387,9 @@ __device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_tra
 					}
 					d_travel = 0.;
 				}
-			} while (q_new == q_i && r_new == r_i && p0.z <= c.z[nm]);
+				if (!(q_new == q_i && r_new == r_i && p0.z <= c.z[nm]))
+					break;
+			}
 
 			if (fabs(q_new) > n_shells || fabs(r_new) > n_shells || fabs(-1. * q_new - r_new) > n_shells || p0.z > c.z[nm]) {
 				r_cntr = (int)r_new;
@@ -1070,6 +1111,7 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	P.c.nE = nE;
 	P.c.mono = o->mono;
 	P.c.monotonic = o->monotonic;
+	P.c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
 	P.c.n_shells = o->n_shells;
 	P.c.sig_rough = o->sig_rough;
 	P.c.z = o->d_z; P.c.cap = o->d_cap; P.c.ext = o->d_ext; P.c.hexz = o->d_hexz; P.c.ec = o->d_ec;
@@ -1240,6 +1282,7 @@ extern "C" int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const doubl
 {
 	LkCtx c{};
 	c.nmax = o->nmax; c.nE = o->nE; c.mono = o->mono; c.monotonic = o->monotonic; c.n_shells = o->n_shells; c.sig_rough = o->sig_rough;
+	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
 	const size_t nE = (size_t)o->nE, stride = 11 + nE;
 	*leak_rec = nullptr;
@@ -1280,6 +1323,7 @@ extern "C" int pcb_leak_unit_trace_wall(const pcb_leak_optic *o, const double in
 {
 	LkCtx c{};
 	c.nmax = o->nmax; c.nE = o->nE; c.mono = o->mono; c.monotonic = o->monotonic; c.n_shells = o->n_shells; c.sig_rough = o->sig_rough;
+	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
 	DevMem M;
 	double *d_in, *d_out;
