@@ -339,12 +339,6 @@ extern "C" double polycap_scalar(polycap_vector3 a, polycap_vector3 b) { return 
 
 /* ------------------------------------------------------------------ replay plumbing shared by launch / launch_batch */
 
-struct ReplayOut {
-	std::vector<int> ret;
-	std::vector<double> state; /* [n][11] */
-	std::vector<int64_t> irefl;
-};
-
 /* photon.c:390-955 */
 extern "C" int polycap_photon_launch(polycap_photon *photon, size_t n_energies, double *energies, double **weights, bool leak_calc,
 				     polycap_error **error)
@@ -386,9 +380,9 @@ extern "C" int polycap_photon_launch(polycap_photon *photon, size_t n_energies, 
 
 	std::lock_guard<std::mutex> lock(g_gpu_mutex);
 	pcb_gpu_optic *g = optic_for(d, n_energies, energies, NULL, NULL, -1, error, "polycap_photon_launch");
-	if (!g) {
-		for (size_t i = 0; i < n_energies; i++)
-			(*weights)[i] = 1.;
+	if (!g) { /* no device / no optical constants: nothing was traced, the caller gets no weight vector to free */
+		free(*weights);
+		*weights = NULL;
 		return -1;
 	}
 	int ret = -1;
@@ -407,6 +401,8 @@ extern "C" int polycap_photon_launch(polycap_photon *photon, size_t n_energies, 
 	if (rc) {
 		gpu_fail(error, "polycap_photon_launch");
 		free(lrec);
+		free(*weights);
+		*weights = NULL;
 		return -1;
 	}
 	/* the reference normalises start_direction in place: once in launch (photon.c:492) and once per capil_trace call (capil.c:1237) */
@@ -880,7 +876,8 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 			const char *ce = getenv("POLYCAP_B200_CHUNKS");
 			int64_t chunks = ce ? atoll(ce) : (int64_t)((rf_bytes + rw_bytes) / ((size_t)48 << 20));
 			chunks = std::max<int64_t>(1, std::min<int64_t>(8, chunks));
-			chunk_ids = std::max<int64_t>((n_ids + chunks - 1) / chunks, (int64_t)G * 65536);
+			/* a wave should refill every CTA's photon pool (148 x 1152 slots) a few times: shorter launches are mostly ramp-up and tail */
+			chunk_ids = std::max<int64_t>((n_ids + chunks - 1) / chunks, ce ? (int64_t)G * 65536 : (int64_t)G * 450000);
 		}
 		if (!leak_calc && chunk_ids > 0 && n_ids > chunk_ids + chunk_ids / 4)
 			n_ids = chunk_ids;
