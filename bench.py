@@ -285,6 +285,7 @@ def measure_device(ctx, pc, src, nE, ids_per_step, steps, warmup, clocks=False, 
 
     for k in range(warmup):
         step(k)
+    allreduce_tallies(t_sum, t_cnt)  # warm the collective too (first use sets up the communicator's channels)
     barrier(ctx)
     ses.trace_ms()  # drop warm-up timings
     k0 = ses.kernels()
@@ -615,13 +616,14 @@ def main():
         barrier(ctx)
         if rank == 0:
             try:
-                one_process = {"what": "polycap_source_get_transmission_efficiencies called ONCE per step by rank 0 with POLYCAP_B200_DEVICES=all: the library "
-                                       "shards the photon ids over the %d devices, cuts the id-ordered stream at the n-th exit across them and sums the tallies "
+                one_process = {"what": "polycap_source_get_transmission_efficiencies called ONCE per step by rank 0 with POLYCAP_B200_DEVICES=0,..,N-1: the library "
+                                       "shards the photon ids over the %d devices of this run, cuts the id-ordered stream at the n-th exit across them and sums the tallies "
                                        "over peer memory (NVLink); the other ranks idle" % world}
-                one_process[args.workload] = measure_e2e(ctx, pc, src, nE, n_exit * world, max(1, min(args.steps, 5)), devices="all", all_ranks=False)
+                devs = ",".join(str(i) for i in range(world))  # the N devices of this run, not every device of the box
+                one_process[args.workload] = measure_e2e(ctx, pc, src, nE, n_exit * world, max(1, min(args.steps, 5)), devices=devs, all_ranks=False)
                 wx = WORKLOADS["xos1"]
                 nx = len(wx["energies"])
-                one_process["xos1"] = measure_e2e(ctx, pc, build_source(pc, wx), nx, min(200_000 * world, 2_000_000_000 // (8 * (17 + nx))), 3, devices="all",
+                one_process["xos1"] = measure_e2e(ctx, pc, build_source(pc, wx), nx, min(200_000 * world, 2_000_000_000 // (8 * (17 + nx))), 3, devices=devs,
                                                   all_ranks=False)
             except Exception as exc:
                 one_process = {"error": "%s: %s" % (type(exc).__name__, exc)}

@@ -875,6 +875,10 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		if (chunk_ids == 0 && exit_frac > 0) {
 			const char *ce = getenv("POLYCAP_B200_CHUNKS");
 			int64_t chunks = ce ? atoll(ce) : (int64_t)((rf_bytes + rw_bytes) / ((size_t)48 << 20));
+			/* splitting pays only where the records are a sizeable part of a wave's traffic: below ~256 record bytes per photon id
+			 * (short grids, low exit fractions) the download hides behind nothing worth hiding and smaller waves only trace less well */
+			if (!ce && exit_frac * (17.0 + (double)nE) * 8.0 < 256.0)
+				chunks = 1;
 			chunks = std::max<int64_t>(1, std::min<int64_t>(8, chunks));
 			/* a wave should refill every CTA's photon pool (148 x 1152 slots) a few times: shorter launches are mostly ramp-up and tail */
 			chunk_ids = std::max<int64_t>((n_ids + chunks - 1) / chunks, ce ? (int64_t)G * 65536 : (int64_t)G * 450000);

@@ -102,6 +102,7 @@ struct pcb_gpu_optic {
 	double *d_rin = nullptr;
 	/* two-phase waves (multi-device runs, pipelined record download): the optic's own streams and a pinned word block the
 	 * device copies wave counts into ([0] ids below the cut, [1] exits below the cut, [2] exits of the whole wave) */
+	double *d_reduce = nullptr; /* output of tally_reduce_peers (nE doubles + the counter block) */
 	cudaStream_t s_main = nullptr, s_copy = nullptr;
 	cudaEvent_t ev_fin = nullptr, ev_copy = nullptr;
 	int64_t *h_pin = nullptr;
@@ -273,6 +274,7 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	cudaFreeHost(g->h_ec);
 	cudaFreeHost(g->h_stage);
 	cudaFreeHost(g->h_pin);
+	cudaFree(g->d_reduce);
 	if (g->s_main) cudaStreamDestroy(g->s_main);
 	if (g->s_copy) cudaStreamDestroy(g->s_copy);
 	if (g->ev_fin) cudaEventDestroy(g->ev_fin);
@@ -1079,17 +1081,16 @@ extern "C" int pcb_gpu_reduce_tallies(pcb_gpu_optic *const *optics, double *cons
 			pp.sum[k] = d_sum[k];
 			pp.cnt[k] = d_cnt[k];
 		}
-		double *out = nullptr;
-		CK(cudaMalloc(&out, (size_t)nE * 8 + PCB_C_COUNT * 8));
+		if (!g0->d_reduce)
+			CK(cudaMalloc(&g0->d_reduce, (size_t)nE * 8 + PCB_C_COUNT * 8));
+		double *out = g0->d_reduce;
 		int64_t *out_c = (int64_t *)(out + nE);
 		const int nt = nE > PCB_C_COUNT ? nE : PCB_C_COUNT;
-		tally_reduce_peers<<<(nt + 255) / 256, 256>>>(pp, nE, out, out_c);
+		tally_reduce_peers<<<(nt + 255) / 256, 256, 0, g0->s_main>>>(pp, nE, out, out_c);
 		g0->n_kernels++;
-		cudaError_t e1 = cudaMemcpy(h_sum, out, (size_t)nE * 8, cudaMemcpyDeviceToHost);
-		cudaError_t e2 = cudaMemcpy(h_cnt, out_c, PCB_C_COUNT * 8, cudaMemcpyDeviceToHost);
-		cudaFree(out);
-		CK(e1);
-		CK(e2);
+		CK(cudaMemcpyAsync(h_sum, out, (size_t)nE * 8, cudaMemcpyDeviceToHost, g0->s_main));
+		CK(cudaMemcpyAsync(h_cnt, out_c, PCB_C_COUNT * 8, cudaMemcpyDeviceToHost, g0->s_main));
+		CK(cudaStreamSynchronize(g0->s_main));
 		return 0;
 	}
 	std::vector<double> ts((size_t)nE);
