@@ -465,9 +465,10 @@ def leak_record(ctx, pc, w, n_exit, cpu_seconds):
     out = {"workload": w["desc"] + " -- leak_calc = true", "n_energies": nE, "value": started / dt, "unit": "photons/s", "seconds": dt, "exits": exits,
            "simulated_photons": started, "external_leak_records": n_ext, "internal_leak_records": n_int,
            "reflection_events_incl_secondaries": cnt.get("refl_all"), "wall_march_steps": cnt.get("wall_steps"),
+           "wall_march_steps_evaluated": cnt.get("q_hit_batches"),
            "roofline": {"bound": "fp64", "achieved": flops / dt / 1e12, "peak": ctx.dfma_peak, "unit": "TFLOP/s", "frac": flops / dt / 1e12 / ctx.dfma_peak if ctx.dfma_peak else None,
-                        "model": "155*launched + 445*refl + 76*nE*refl + 100*exit + 60*wall_steps (SURVEY 8d, leak terms); segment steps of the leak tracer are not counted",
-                        "kernel": "pcb_leak_kernel (one thread per primary photon, explicit frame stack)"}}
+                        "model": "155*launched + 445*refl + 76*nE*refl + 100*exit + 60*wall_steps (SURVEY 8d, leak terms; wall_steps = the steps of the reference's march, of which only wall_march_steps_evaluated are walked, the rest is jumped over exactly); segment steps of the leak tracer are not counted",
+                        "kernel": "pcb_leak_kernel (one warp per primary photon: energies and segment scan dealt over the lanes, wall march jumped; explicit frame stack)"}}
     try:
         ref, rsrc = reference_setup(w)
         with quiet_stdout():

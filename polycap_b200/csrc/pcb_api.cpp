@@ -891,10 +891,10 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		if (leak_calc) {
 			double *lrec = NULL;
 			int64_t n_lrec = 0;
-			/* a leak wave also holds ~24 leak records of 11+nE doubles per id (pcb_leak.cu): its own bytes-per-id budget, 8 GB per wave;
-			 * a wave whose record pool still overflows (thin walls, hard photons) is retried with half the ids */
-			const int64_t leak_bytes_per_id = wave_bytes_per_id + 24 * (11 + (int64_t)nE) * 8;
-			const int64_t leak_wave_max = std::max<int64_t>(1024, std::min<int64_t>(wave_max, ((int64_t)8 << 30) / leak_bytes_per_id));
+			/* a leak wave also holds room for 96 leak records of 11+nE doubles per id (pcb_leak.cu): its own bytes-per-id budget, 24 GB per
+			 * wave; a wave whose record pool still overflows (thin walls, hard photons) is retried with half the ids */
+			const int64_t leak_bytes_per_id = wave_bytes_per_id + 96 * (11 + (int64_t)nE) * 8;
+			const int64_t leak_wave_max = std::max<int64_t>(1024, std::min<int64_t>(wave_max, ((int64_t)24 << 30) / leak_bytes_per_id));
 			if (n_ids > leak_wave_max)
 				n_ids = leak_wave_max;
 			if (leak_shrink > 1)

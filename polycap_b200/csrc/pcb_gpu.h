@@ -41,6 +41,7 @@ enum {
 	PCB_C_SOLVES,           /* full quadratic solves */
 	PCB_C_LAUNCHED,
 	/* 10..14: scheduler statistics of the task-queue tracer (batches, lanes, empty polls, lost races, HIT batches) */
+	PCB_C_WALL_EVALS = 14,  /* leak runs (the slot is a scheduler statistic otherwise): wall-march steps actually evaluated, the rest was jumped over */
 	PCB_C_WALL_STEPS = 15,  /* leak runs: steps of the wall march (capil.c:1018-1068) */
 	PCB_C_COUNT = 16
 };

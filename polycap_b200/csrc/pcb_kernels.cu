@@ -1133,7 +1133,7 @@ extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *co
 	std::vector<int8_t> st((size_t)n);
 	std::vector<int> ir((size_t)n), ln((size_t)n);
 	std::vector<double> f((size_t)n * 11);
-	int64_t work[2] = {0, 0};
+	int64_t work[4] = {0, 0, 0, 0};
 	if (pcb_leak_run(&v, nullptr, 0, 0, n, coords, dir, ev, st.data(), ir.data(), f.data(), weights, ln.data(), leak_rec, n_leak_rec, work)) {
 		g_last_error = pcb_leak_last_error();
 		return -1;
@@ -1158,6 +1158,8 @@ extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *co
 		counters[PCB_C_REFL_ALL] = work[0];
 		counters[PCB_C_LAUNCHED] = n;
 		counters[PCB_C_WALL_STEPS] = work[1];
+		counters[PCB_C_WALL_EVALS] = work[2];
+		counters[PCB_C_SOLVES] = work[3];
 	}
 	return 0;
 }
@@ -1180,7 +1182,7 @@ extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s,
 	std::vector<int> ir((size_t)n_ids), ln((size_t)n_ids);
 	std::vector<double> f((size_t)n_ids * 17), w((size_t)n_ids * nE);
 	double *recs = nullptr;
-	int64_t nrec = 0, work[2] = {0, 0};
+	int64_t nrec = 0, work[4] = {0, 0, 0, 0};
 	if (int lrc = pcb_leak_run(&v, s, seed, id0, n_ids, nullptr, nullptr, nullptr, st.data(), ir.data(), f.data(), w.data(), ln.data(), &recs, &nrec, work)) {
 		g_last_error = pcb_leak_last_error();
 		return lrc; /* -2: record pool full, the caller retries with a smaller wave */
@@ -1192,6 +1194,7 @@ extern "C" int pcb_gpu_run_wave_leak(pcb_gpu_optic *g, const pcb_source_desc *s,
 	wc.reflections = (unsigned long long)work[0];
 	wc.launched = (unsigned long long)n_ids;
 	wc.dbg[5] = (unsigned long long)work[1]; /* -> counters[PCB_C_WALL_STEPS] */
+	wc.dbg[4] = (unsigned long long)work[2]; /* -> counters[PCB_C_WALL_EVALS] */
 	bool ok = cudaMemcpy(g->d_status, st.data(), (size_t)n_ids, cudaMemcpyHostToDevice) == cudaSuccess &&
 		  cudaMemcpy(g->d_irefl, ir.data(), (size_t)n_ids * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
 		  cudaMemcpy(g->d_fields, f.data(), f.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&

@@ -1,23 +1,11 @@
 /*
- * pcb_leak.cu -- photon transport WITH leak / recap wall transport (leak_calc = true), sm_100a, FP64.
+ * pcb_leak.cu -- kernels and host driver of the leak / recap transport (leak_calc = true), sm_100a, FP64.
  *
- * Reference behaviour reproduced (paths relative to /root/reference):
- *   polycap_capil_trace_wall      src/polycap-capil.c:896-1194   march through the glass to the next bore / out of the optic
- *   polycap_photon_pc_intersect   src/polycap-photon.c:174-362   where a photon left through the outer hexagonal surface
- *   polycap_capil_reflect (leak)  src/polycap-capil.c:565-891    leak weights, ext/int leak records, the secondary ("recap")
- *                                                                photon that continues in the neighbouring capillary
- *   polycap_capil_trace           src/polycap-capil.c:1197-1361  with the per-segment in-optic checks
- *   polycap_photon_launch (leak)  src/polycap-photon.c:645-907   photons that start in the glass
- *
- * One thread owns one primary photon (persistent threads pull ids from a global counter).  The reference recurses --
- * capil_reflect creates a secondary photon and runs capil_trace on it, whose capil_reflect may create another -- which
- * here is an explicit frame stack per thread: a frame is a photon with its weight vector, capillary axis, segment
- * index and trace-loop counter; a parent waits in its frame while its secondary runs.  Leak records are streamed in
- * depth-first order into the thread's record strip, which preserves the reference's order within the external and
- * the internal list (the two lists are independent), and are rolled back when the reference discards a secondary's
- * leaks (capil.c:799-805).  All trajectory arithmetic uses the bit-faithful primitives of pcb_math.h; weights use the
- * reference-order Fresnel term.  This path favours fidelity over speed (the reference's leak mode is ~1000x slower
- * than its plain mode); the voted, cheap-weights tracer of pcb_trace.cuh serves leak_calc = false.
+ * The per-photon state machine -- wall march, leak weights, secondary photons, the reference lines each part follows -- is
+ * pcb_leak_core.cuh.  Here: pcb_leak_kernel (persistent warps, ONE WARP per primary photon pulling ids from a global counter;
+ * a warp's frame stack, weight arena and record strip live in global memory), the single-item kernels behind the reference's
+ * TEST_BUILD entry points, and the host side that sizes workspaces from a memory budget and returns the records in id order.
+ * The voted, cheap-weights tracer of pcb_trace2.cuh serves leak_calc = false.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -25,842 +13,20 @@
 #include <string>
 #include <vector>
 
+#ifdef LK_OUTLINE /* tuning builds: one copy of the solve, the reflection geometry and the normalisation (see LK_DEV in pcb_leak_core.cuh) */
+#define PCB_OUTLINE_HOT 1
+#define PCB_NORM3_CALL 1
+#endif
 #include "pcb_device.cuh"
 #include "pcb_gpu.h"
 #include "pcb_leak.h"
+#include "pcb_leak_core.cuh"
 
-/* Capacities per primary photon.  A hard photon at a steep angle crosses capillary after capillary, each crossing one
- * nested secondary (the reference recurses just as deep: its corpus shows 440 leak records and i_refl 568 on one photon). */
-#define LK_DEPTH 1400    /* frames: primary + nested secondaries */
-#define LK_REC_CAP 2048  /* leak records */
 #define LK_THREADS 128
-
-enum { LK_ERR_DEPTH = 1, LK_ERR_RECORDS = 2, LK_ERR_POOL = 4 }; /* RECORDS: one photon exceeds LK_REC_CAP leaks; POOL: the wave's record pool is full */
-
-struct LkCtx {
-	int nmax, nE, mono, monotonic;
-	int no_fast_march; /* POLYCAP_B200_LEAK_FULL_MARCH=1: every step of the wall march takes the reference's full step (checking aid) */
-	double n_shells, sig_rough;
-	const double *z, *cap, *ext, *hexz; /* global */
-	const double *ec;                   /* [EC_ROWS][nE] */
-};
-
-struct LkFrame {
-	V3 ec, ed, ev;       /* exit_coords, exit_direction, exit_electric_vector */
-	long long irefl;
-	double dtrav;
-	double A, B;         /* capillary axis: cap_x[i] = A*hexz[i], cap_y[i] = B*hexz[i] */
-	int ix, it, it_end;  /* segment index, trace-loop counter (photon.c:912, capil.c:785) */
-	int last_esc;
-	/* saved while a secondary runs */
-	V3 sn;
-	double cosalfa;
-	int iesc_after, rec_mark, cont;
-	double *w;
-};
-
-enum { CONT_TRACE = 0, CONT_FACE = 1, CONT_UNIT = 2 };
-
-struct LkOut {
-	double *rec;    /* this thread's strip: cap x (11+nE) */
-	int nrec;
-	int err;
-	int cap;        /* records the strip holds */
-	int depth;      /* frames this thread's stack holds */
-	/* pool of full-size workspaces (LK_DEPTH frames, LK_REC_CAP records) a photon moves to when it outgrows the thread's small one */
-	LkFrame *big_frames;
-	double *big_arena, *big_rec;
-	unsigned long long *big_next;
-	unsigned long long big_n;
-};
-
-/* The photon's nesting is about to exceed the thread's small workspace: move its frames [0, sp], their weight vectors and its
- * records to a full-size workspace from the pool and carry on there.  false: already full-size, or the pool is used up. */
-__device__ bool lk_grow(const LkCtx &c, LkOut &o, LkFrame *&fr, double *&arena, int sp)
-{
-	if (o.depth >= LK_DEPTH || !o.big_next)
-		return false;
-	const unsigned long long idx = atomicAdd(o.big_next, 1ULL);
-	if (idx >= o.big_n)
-		return false;
-	const size_t nE = (size_t)c.nE, stride = 11 + nE;
-	LkFrame *nf = o.big_frames + idx * (unsigned long long)LK_DEPTH;
-	double *na = o.big_arena + idx * (unsigned long long)(LK_DEPTH + 1) * nE;
-	double *nr = o.big_rec + idx * (unsigned long long)LK_REC_CAP * stride;
-	for (size_t k = 0; k < (size_t)(sp + 1) * nE; k++)
-		na[k] = arena[k];
-	for (int k = 0; k <= sp; k++) {
-		nf[k] = fr[k];
-		nf[k].w = na + (fr[k].w - arena);
-	}
-	for (size_t k = 0; k < (size_t)o.nrec * stride; k++)
-		nr[k] = o.rec[k];
-	fr = nf;
-	arena = na;
-	o.rec = nr;
-	o.cap = LK_REC_CAP;
-	o.depth = LK_DEPTH;
-	return true;
-}
-
-__device__ __forceinline__ int lk_z_index(const LkCtx &c, double zq) /* last i < nmax with z[i] <= zq, 0 when none */
-{
-	if (c.monotonic) {
-		if (!(c.z[0] <= zq))
-			return 0;
-		int lo = 0, hi = c.nmax - 1; /* invariant: z[lo] <= zq */
-		while (lo < hi) {
-			int mid = (lo + hi + 1) >> 1;
-			if (c.z[mid] <= zq)
-				lo = mid;
-			else
-				hi = mid - 1;
-		}
-		return lo;
-	}
-	int id = 0;
-	for (int i = 0; i < c.nmax; i++)
-		if (c.z[i] <= zq)
-			id = i;
-	return id;
-}
-
-__device__ __forceinline__ int lk_z_index_incl(const LkCtx &c, double zq) /* last i <= nmax with z[i] <= zq (photon.c:626, capil.c:747) */
-{
-	int ix = 0;
-	if (c.monotonic) {
-		ix = lk_z_index(c, zq);
-		if (c.z[c.nmax] <= zq)
-			ix = c.nmax;
-		return ix;
-	}
-	for (int i = 0; i <= c.nmax; i++)
-		if (c.z[i] <= zq)
-			ix = i;
-	return ix;
-}
-
-__device__ __forceinline__ V3 lk_propagate(const V3 &p, const V3 &d, double zt)
-{
-	V3 r;
-	r.x = p.x + d.x * (zt - p.z) / d.z;
-	r.y = p.y + d.y * (zt - p.z) / d.z;
-	r.z = zt;
-	return r;
-}
-
-__device__ void lk_append(const LkCtx &c, LkOut &o, int kind, const V3 &co, const V3 &di, const V3 &el, long long nrefl, const double *w)
-{
-	if (o.nrec >= o.cap) {
-		o.err |= LK_ERR_RECORDS;
-		return;
-	}
-	double *r = o.rec + (size_t)o.nrec * (11 + c.nE);
-	r[0] = (double)kind;
-	r[1] = co.x; r[2] = co.y; r[3] = co.z;
-	r[4] = di.x; r[5] = di.y; r[6] = di.z;
-	r[7] = el.x; r[8] = el.y; r[9] = el.z;
-	r[10] = (double)nrefl;
-	for (int e = 0; e < c.nE; e++)
-		r[11 + e] = w[e];
-	o.nrec++;
-}
-
-/* photon.c:174-362 */
-__device__ int lk_pc_intersect(const LkCtx &c, V3 coord, V3 direction, V3 &out)
-{
-	if (direction.z == 0.)
-		return 0;
-	V3 bd = {-1. * direction.x, -1. * direction.y, -1. * direction.z};
-	norm3(bd);
-	int z_id = lk_z_index(c, coord.z);
-	double ext_here = (c.ext[z_id + 1] - c.ext[z_id]) / (c.z[z_id + 1] - c.z[z_id]) * (coord.z - c.z[z_id]) + c.ext[z_id];
-	if (within_pc(ext_here, coord.x, coord.y) == 1)
-		return 0;
-	int step;
-	if (bd.z < 0.) {
-		z_id = z_id + 1;
-		step = -1;
-	} else {
-		step = 1;
-	}
-	bool found = false;
-	const int in0 = within_pc(ext_here, coord.x, coord.y);
-	do {
-		z_id += step;
-		if (z_id < 0 || z_id > c.nmax)
-			break;
-		double px = coord.x + bd.x * (c.z[z_id] - coord.z) / bd.z;
-		double py = coord.y + bd.y * (c.z[z_id] - coord.z) / bd.z;
-		if (in0 != within_pc(c.ext[z_id], px, py)) {
-			found = true;
-			break;
-		}
-	} while (z_id >= 0 && z_id <= c.nmax);
-	if (!found)
-		return 0;
-	int zb = z_id, ze = z_id - step;
-	if (ze < 0 || ze > c.nmax)
-		return 0;
-	V3 beg, end;
-	beg.x = coord.x + bd.x * (c.z[zb] - coord.z) / bd.z;
-	beg.y = coord.y + bd.y * (c.z[zb] - coord.z) / bd.z;
-	beg.z = coord.z + bd.z * (c.z[zb] - coord.z) / bd.z;
-	end.x = coord.x + bd.x * (c.z[ze] - coord.z) / bd.z;
-	end.y = coord.y + bd.y * (c.z[ze] - coord.z) / bd.z;
-	end.z = coord.z + bd.z * (c.z[ze] - coord.z) / bd.z;
-	double hb = sqrt((c.ext[zb] * c.ext[zb]) - ((c.ext[zb] / 2.) * (c.ext[zb] / 2.)));
-	double he = sqrt((c.ext[ze] * c.ext[ze]) - ((c.ext[ze] / 2.) * (c.ext[ze] / 2.)));
-	double pb[3], pe[3], zs[3];
-	pb[0] = fabs(0 * beg.x + 1 * beg.y);
-	pb[1] = fabs(PCB_COSPI_6 * beg.x + 0.5 * beg.y);
-	pb[2] = fabs(PCB_COSPI_6 * beg.x + -0.5 * beg.y);
-	pe[0] = fabs(0 * end.x + 1 * end.y);
-	pe[1] = fabs(PCB_COSPI_6 * end.x + 0.5 * end.y);
-	pe[2] = fabs(PCB_COSPI_6 * end.x + -0.5 * end.y);
-	for (int k = 0; k < 3; k++)
-		zs[k] = (pb[k] - hb) / (hb - he - pb[k] + pe[k]) * (c.ext[zb] - c.ext[ze]) + c.ext[zb];
-	double lo = (step < 0) ? c.z[zb] : c.z[ze];
-	double hi = (step < 0) ? c.z[ze] : c.z[zb];
-	bool have = false;
-	double zf = 0;
-	for (int k = 0; k < 3; k++) {
-		if (!(zs[k] >= lo && zs[k] <= hi))
-			continue;
-		if (!have) {
-			zf = zs[k];
-			have = true;
-		} else if (step < 0 ? (zs[k] > zf) : (zs[k] < zf)) {
-			zf = zs[k];
-		}
-	}
-	if (!have) {
-		out = end;
-		return 1;
-	}
-	out.x = coord.x + bd.x * (zf - coord.z) / bd.z;
-	out.y = coord.y + bd.y * (zf - coord.z) / bd.z;
-	out.z = coord.z + bd.z * (zf - coord.z) / bd.z;
-	return 1;
-}
-
-/* classification once a wall march ends without a new bore: 3 = out the side, 2 = exit face in the glass (capil.c:1076-1107, 1150-1186) */
-__device__ int lk_wall_exit_class(const LkCtx &c, const V3 &ec, const V3 &ed, const V3 &fallback, double &d_travel)
-{
-	const int nm = c.nmax;
-	V3 at_exit = lk_propagate(ec, ed, c.z[nm]);
-	V3 rel;
-	if (within_pc(c.ext[nm], at_exit.x, at_exit.y) == 0) {
-		V3 side;
-		if (lk_pc_intersect(c, at_exit, ed, side)) {
-			rel.x = side.x - ec.x; rel.y = side.y - ec.y; rel.z = side.z - ec.z;
-		} else {
-			rel.x = fallback.x - ec.x; rel.y = fallback.y - ec.y; rel.z = fallback.z - ec.z;
-		}
-		d_travel = sqrt(dot3(rel, rel));
-		return 3;
-	}
-	rel.x = fallback.x - ec.x; rel.y = fallback.y - ec.y; rel.z = fallback.z - ec.z;
-	d_travel = sqrt(dot3(rel, rel));
-	return 2;
-}
-
-__device__ __forceinline__ int lk_segment_checked(const V3 &c0, const V3 &c1, double r0, double r1, const V3 &p0, const V3 &dir, V3 &hit, V3 &sn)
-{
-	if (c0.z < 0. || c1.z < 0 || r0 < 0. || r1 < 0. || dir.z < 0 || c1.z <= c0.z) { /* capil.c:65-100 */
-		sn.x = sn.y = sn.z = 0.0;
-		return -1;
-	}
-	V3 h = hit;
-	int r = segment_solve(c0, c1, r0, r1, p0, dir, hit.z, h, sn);
-	if (r == 1)
-		hit = h;
-	return r;
-}
-
-/* capil.c:896-1194; ed is normalised in place like the reference does with photon->exit_direction */
-__device__ int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel, int &r_cntr, int &q_cntr, unsigned long long &n_steps)
-{
-	const int nm = c.nmax;
-	d_travel = 0.;
-	r_cntr = 0;
-	q_cntr = 0;
-	norm3(ed);
-	if (ec.z >= c.z[nm])
-		return -2;
-	int z_id = lk_z_index(c, ec.z);
-	double ext_here;
-	if (c.z[z_id] != ec.z)
-		ext_here = ((c.ext[z_id + 1] - c.ext[z_id]) / (c.z[z_id + 1] - c.z[z_id])) * (ec.z - c.z[z_id]) + c.ext[z_id];
-	else
-		ext_here = c.ext[z_id];
-	V3 hit = ec, sn;
-	const double n_shells = c.n_shells;
-	if (n_shells == 0.) {
-		if (sqrt((ec.x) * (ec.x) + (ec.y) * (ec.y)) > ext_here)
-			return -2;
-	} else if (within_pc(ext_here, ec.x, ec.y) == 0) {
-		return -2;
-	}
-	double hexz = ext_here / (2. * PCB_COSPI_6 * (n_shells + 1));
-	double q_i, r_i, q_new = 0, r_new = 0;
-	hex_cell(hexz, ec.x, ec.y, q_i, r_i);
-	int iesc = 0;
-	V3 c0, c1, p0;
-	if (n_shells == 0.) { /* capil.c:992-1013 */
-		do {
-			p0 = lk_propagate(ec, ed, c.z[z_id]);
-			c0.x = 0.; c0.y = 0.; c0.z = c.z[z_id];
-			c1.x = 0.; c1.y = 0.; c1.z = c.z[z_id + 1];
-			iesc = lk_segment_checked(c0, c1, c.cap[z_id], c.cap[z_id + 1], p0, ed, hit, sn);
-			z_id++;
-		} while (iesc != 1 && z_id < nm - 1);
-	} else {
-		double dist = 0;
-		for (;;) {
-			/* March in steps of a tenth of the bore radius until the hex cell changes (capil.c:1018-1068).  A step is eventful when the point
-			 * falls back into the photon's own bore, leaves its hexagonal cell or passes the end of the optic; between the bore wall and
-			 * the cell boundary thousands of steps are none of that.  Such a step is recognised from the squared distance to the cell's
-			 * axis and the three edge normals of the hexagon (bounds taken 1e-9 inside the safe zone, rounding differences to the
-			 * reference's own expressions are ~1e-16) and then only advances the path length and the z index, exactly as the reference
-			 * does; everything else takes the reference's full step, so the outcome is the reference's step for step. */
-			const bool fast_ok = c.monotonic && ed.z >= 0. && !c.no_fast_march;
-			const double inv_den = 1.0 / (2. * PCB_COSPI_6 * (n_shells + 1));
-			const double Ai = (2. * q_i + r_i) * PCB_COSPI_6, Bi = r_i * (3. / 2);
-			int zc = -1;
-			double seg_z0 = 0, seg_e0 = 0, seg_c0 = 0, seg_se = 0, seg_sc = 0;
-			for (;;) {
-				n_steps++;
-				dist += c.cap[z_id] / 10.;
-				if (fast_ok) {
-					const double p0z = ec.z + dist * ed.z;
-					int zi = z_id;
-					if (!(c.z[zi] <= p0z))
-						zi = lk_z_index(c, p0z);
-					while (zi + 1 < nm && c.z[zi + 1] <= p0z)
-						zi++;
-					if (zi != zc) {
-						zc = zi;
-						seg_z0 = c.z[zi];
-						const double dz = c.z[zi + 1] - seg_z0;
-						seg_e0 = c.ext[zi];
-						seg_c0 = c.cap[zi];
-						seg_se = (c.ext[zi + 1] - seg_e0) / dz;
-						seg_sc = (c.cap[zi + 1] - seg_c0) / dz;
-					}
-					const double t = p0z - seg_z0;
-					const double hz = (seg_se * t + seg_e0) * inv_den;
-					const double rr = (seg_sc * t + seg_c0) * (1. + 1.e-9);
-					const double ux = (ec.x + dist * ed.x) - Ai * hz, uy = (ec.y + dist * ed.y) - Bi * hz;
-					const double h = PCB_COSPI_6 * hz * (1. - 1.e-9);
-					if (rr > 0. && hz > 0. && ux * ux + uy * uy > rr * rr && fabs(ux) < h && fabs(0.5 * ux + PCB_COSPI_6 * uy) < h &&
-					    fabs(0.5 * ux - PCB_COSPI_6 * uy) < h && p0z <= c.z[nm]) {
-						z_id = zi;
-						continue;
-					}
-				}
-				p0.x = ec.x + dist * ed.x;
-				p0.y = ec.y + dist * ed.y;
-				p0.z = ec.z + dist * ed.z;
-				if (c.monotonic && ed.z >= 0.) { /* the march only moves forward: the index follows incrementally */
-					if (!(c.z[z_id] <= p0.z))
-						z_id = lk_z_index(c, p0.z);
-					while (z_id + 1 < nm && c.z[z_id + 1] <= p0.z)
-						z_id++;
-				} else {
-					z_id = lk_z_index(c, p0.z);
-				}
-				ext_here = ((c.ext[z_id + 1] - c.ext[z_id]) / (c.z[z_id + 1] - c.z[z_id])) * (p0.z - c.z[z_id]) + c.ext[z_id];
-				double rad_here = ((c.cap[z_id + 1] - c.cap[z_id]) / (c.z[z_id + 1] - c.z[z_id])) * (p0.z - c.z[z_id]) + c.cap[z_id];
-				hexz = ext_here / (2. * PCB_COSPI_6 * (n_shells + 1));
-				hex_cell(hexz, p0.x, p0.y, q_new, r_new);
-				c0.y = r_i * (3. / 2) * hexz;
-				c0.x = (2. * q_i + r_i) * PCB_COSPI_6 * hexz;
-				double d0 = sqrt((p0.x - c0.x) * (p0.x - c0.x) + (p0.y - c0.y) * (p0.y - c0.y));
-				if (d0 < rad_here && fabs(q_i) <= n_shells && fabs(r_i) <= n_shells && fabs(-1. * q_i - r_i) <= n_shells) {
-					V3 rel = {p0.x - ec.x, p0.y - ec.y, p0.z - ec.z};
-					d_travel = sqrt(dot3(rel, rel));
-					if (d_travel > 1.e-5) {
-						r_cntr = (int)r_i;
-						q_cntr = (int)q_i;
-						return 1;
-					}
-					d_travel = 0.;
-				}
-				if (!(q_new == q_i && r_new == r_i && p0.z <= c.z[nm]))
-					break;
-			}
-
-			if (fabs(q_new) > n_shells || fabs(r_new) > n_shells || fabs(-1. * q_new - r_new) > n_shells || p0.z > c.z[nm]) {
-				r_cntr = (int)r_new;
-				q_cntr = (int)q_new;
-				return lk_wall_exit_class(c, ec, ed, p0, d_travel);
-			}
-			iesc = 0;
-			do { /* scan the segments of the new capillary from z_id on (capil.c:1110-1133) */
-				p0 = lk_propagate(ec, ed, c.z[z_id]);
-				hexz = c.ext[z_id] / (2. * PCB_COSPI_6 * (n_shells + 1));
-				c0.y = r_new * (3. / 2) * hexz;
-				c0.x = (2. * q_new + r_new) * PCB_COSPI_6 * hexz;
-				c0.z = c.z[z_id];
-				hexz = c.ext[z_id + 1] / (2. * PCB_COSPI_6 * (n_shells + 1));
-				c1.y = r_new * (3. / 2) * hexz;
-				c1.x = (2. * q_new + r_new) * PCB_COSPI_6 * hexz;
-				c1.z = c.z[z_id + 1];
-				iesc = lk_segment_checked(c0, c1, c.cap[z_id], c.cap[z_id + 1], p0, ed, hit, sn);
-				z_id++;
-			} while (iesc != 1 && z_id < nm - 1);
-			if (z_id >= nm && iesc != 0) { /* capil.c:1134-1140 */
-				q_i = q_new;
-				r_i = r_new;
-				z_id = nm - 1;
-				continue;
-			}
-			break;
-		}
-	}
-	r_cntr = (int)r_new;
-	q_cntr = (int)q_new;
-	if (iesc != 1) {
-		V3 at_exit = lk_propagate(ec, ed, c.z[nm]);
-		return lk_wall_exit_class(c, ec, ed, at_exit, d_travel);
-	}
-	V3 rel = {hit.x - ec.x, hit.y - ec.y, hit.z - ec.z};
-	d_travel = sqrt(dot3(rel, rel));
-	return (z_id >= nm) ? 2 : 1;
-}
-
-/* one capil_trace call up to (not including) capil_reflect: capil.c:1236-1343.  Returns 1 when a wall hit passed the
- * checks (f.sn / f.cosalfa set, f.ec moved to the hit), otherwise the trace's return code (-1, -2, -3). */
-__device__ int lk_trace_to_hit(const LkCtx &c, LkFrame &f)
-{
-	const int nm = c.nmax;
-	int iesc = 0;
-	norm3(f.ed);
-	V3 last_hit = f.ec;
-	const V3 dir = f.ed;
-	V3 sn = {0, 0, 0};
-	double cosalfa = 0;
-	for (int i = f.ix; i < nm; i++) {
-		V3 c0 = {f.A * c.hexz[i], f.B * c.hexz[i], c.z[i]}, c1 = {f.A * c.hexz[i + 1], f.B * c.hexz[i + 1], c.z[i + 1]};
-		V3 p0 = lk_propagate(f.ec, f.ed, c.z[i]);
-		if (within_pc(c.ext[i], c0.x, c0.y) == 0 || within_pc(c.ext[i + 1], c1.x, c1.y) == 0)
-			return -1;
-		iesc = lk_segment_checked(c0, c1, c.cap[i], c.cap[i + 1], p0, dir, last_hit, sn);
-		cosalfa = dot3(sn, dir);
-		{
-			double ac = pcb_acos(cosalfa);
-			if (ac > PCB_PI / 2. || ac < 0.)
-				iesc = -5;
-		}
-		if (iesc == 1) {
-			double ext_here = ((c.ext[i] - c.ext[i + 1]) / (c.z[i] - c.z[i + 1])) * (last_hit.z - c.z[i + 1]) + c.ext[i + 1];
-			if (c.n_shells == 0.) {
-				if (sqrt(last_hit.x * last_hit.x + last_hit.y * last_hit.y) >= ext_here)
-					return -3;
-			} else if (within_pc(ext_here, last_hit.x, last_hit.y) == 0) {
-				return -3;
-			}
-			f.ix = i + 1;
-			break;
-		} else if (within_pc(c.ext[i], p0.x, p0.y) == 0) {
-			return -3;
-		}
-	}
-	if (iesc != 1)
-		return -2;
-	V3 rel = {last_hit.x - f.ec.x, last_hit.y - f.ec.y, last_hit.z - f.ec.z};
-	f.dtrav += sqrt(dot3(rel, rel));
-	f.ec = last_hit;
-	if (fabs(cosalfa) > 1.0)
-		return -1;
-	{
-		int found = lk_z_index(c, f.ec.z);
-		if (c.z[found] <= f.ec.z) /* no z[i] <= z (NaN photon): the reference leaves *ix = i+1 */
-			f.ix = found;
-	}
-	double ext_here = ((c.ext[f.ix + 1] - c.ext[f.ix]) / (c.z[f.ix + 1] - c.z[f.ix])) * (last_hit.z - c.z[f.ix]) + c.ext[f.ix];
-	if (c.n_shells == 0 && f.ec.x * f.ec.x + f.ec.y * f.ec.y >= ext_here)
-		return -3;
-	if (c.n_shells > 0 && within_pc(ext_here, f.ec.x, f.ec.y) == 0)
-		return -3;
-	f.sn = sn;
-	f.cosalfa = cosalfa;
-	return 1;
-}
-
-struct LkResult {
-	int ret;
-	V3 ec, ed, ev;
-	long long irefl;
-	double dtrav;
-};
-
-/* polycap_photon_launch with leak_calc = true (photon.c:390-955), iterative over an explicit frame stack.
- * `arena` holds (out.depth+1) weight vectors of nE doubles; arena[0..nE) ends up with the primary's weights. */
-/* Single-step use of the state machine (the reference's TEST_BUILD entry points with leak_calc = true): the photon state comes from
- * the caller instead of the launch preamble, and the machine stops when the primary frame has finished
- *   mode 1  one polycap_capil_reflect (capil.c:565-891) on wall normal `normal`: ret = 1 / 0 / -1 / -2
- *   mode 2  one polycap_capil_trace (capil.c:1197-1361):                        ret = 1 / 0 / -1 / -2 / -3 */
-struct LkUnit {
-	int mode;
-	V3 normal;
-	long long irefl;
-	double A, B;
-	int ix;
-};
-
-__device__ void lk_photon(const LkCtx &c, const V3 &sc, V3 sd, const V3 &sev, double d_travel0, LkFrame *&fr, double *&arena, LkOut &out, LkResult &res,
-			  unsigned long long &n_refl_events, unsigned long long &n_wall_steps, const LkUnit *unit = nullptr)
-{
-	const int nm = c.nmax, nE = c.nE;
-	int sp = 0;
-	LkFrame *f = &fr[0];
-	f->w = arena;
-	if (!unit) /* single-step entries arrive with the photon's weights in arena[0, nE) */
-		for (int e = 0; e < nE; e++)
-			f->w[e] = 1.;
-	f->irefl = unit ? unit->irefl : 0;
-	f->dtrav = d_travel0;
-	const V3 raw_dir = sd;
-	norm3(sd);
-	const V3 start_dir = sd;
-	f->ec = sc;
-	f->ed = sd;
-	norm3(f->ed);
-	f->ev = sev;
-	f->last_esc = 0;
-	f->cont = CONT_TRACE;
-	bool glass_start = false; /* photon.c:673-887: started inside the glass at z > 0 */
-	int ret = 0;
-
-	/* ---- launch preamble, photon.c:480-645 ---- */
-	int z_id = 0;
-	if (sc.z > 0)
-		z_id = lk_z_index(c, sc.z);
-	double ext_here = ((c.ext[z_id] - c.ext[z_id + 1]) / (c.z[z_id] - c.z[z_id + 1])) * (sc.z - c.z[z_id]) + c.ext[z_id];
-	double q_i = 0, r_i = 0;
-	bool finished = false;
-	if (c.n_shells == 0.) {
-		if (sqrt((sc.x) * (sc.x) + (sc.y) * (sc.y)) > ext_here) {
-			ret = -2;
-			finished = true;
-		}
-	} else {
-		double hz = ext_here / (2. * PCB_COSPI_6 * (c.n_shells + 1));
-		hex_cell(hz, sc.x, sc.y, q_i, r_i);
-		if (within_pc(ext_here, sc.x, sc.y) == 0) {
-			ret = -2;
-			finished = true;
-		}
-	}
-	enum { S_TRACE_LOOP, S_REFLECT, S_AFTER_REFLECT, S_FRAME_DONE, S_FINISH };
-	int state = S_FINISH, esc = 0, riesc = 0;
-	V3 refl_normal = {0, 0, 1};
-	int unit_ret = -1;
-	if (unit) { /* the caller's photon as it is: no launch preamble */
-		finished = true; /* keeps the launch epilogue out */
-		f->ed = raw_dir; /* capil_reflect / capil_trace normalise it themselves, once */
-		f->A = unit->A;
-		f->B = unit->B;
-		f->ix = unit->ix;
-		f->it = 0;
-		f->it_end = nm;
-		f->sn = unit->normal;
-		f->cosalfa = 0;
-		if (unit->mode == 1) {
-			f->cont = CONT_UNIT;
-			refl_normal = unit->normal;
-			state = S_REFLECT;
-		} else {
-			state = S_TRACE_LOOP;
-		}
-	} else if (!finished) {
-		f->A = (2. * q_i + r_i) * PCB_COSPI_6;
-		f->B = r_i * (3. / 2);
-		f->ix = lk_z_index_incl(c, sc.z);
-		double rad_here, cx_here, cy_here;
-		if (sc.z > 0) {
-			double dz = (c.z[z_id + 1] - c.z[z_id]), off = (sc.z - c.z[z_id]);
-			double cx0 = f->A * c.hexz[z_id], cx1 = f->A * c.hexz[z_id + 1], cy0 = f->B * c.hexz[z_id], cy1 = f->B * c.hexz[z_id + 1];
-			rad_here = ((c.cap[z_id + 1] - c.cap[z_id]) / dz) * off + c.cap[z_id];
-			cx_here = ((cx1 - cx0) / dz) * off + cx0;
-			cy_here = ((cy1 - cy0) / dz) * off + cy0;
-		} else {
-			rad_here = c.cap[0];
-			cx_here = f->A * c.hexz[0];
-			cy_here = f->B * c.hexz[0];
-		}
-		double d_axis = sqrt((sc.x - cx_here) * (sc.x - cx_here) + (sc.y - cy_here) * (sc.y - cy_here));
-		if (d_axis > rad_here) { /* starts in the glass */
-			ret = 2;
-			if (sc.z == 0) { /* photon.c:647-672: reflect off the entrance face, normal (0,0,1) */
-				f->cont = CONT_FACE;
-				refl_normal.x = 0; refl_normal.y = 0; refl_normal.z = 1;
-				state = S_REFLECT;
-			} else { /* photon.c:673-887 */
-				double d_wall = 0;
-				int r_cntr, q_cntr;
-				int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr, n_wall_steps);
-				if (wall_trace <= 0) {
-					ret = -1;
-					state = S_FINISH;
-				} else {
-					for (int e = 0; e < nE; e++)
-						f->w[e] = f->w[e] * exp(-1. * d_wall * c.ec[EC_AMU * nE + e]);
-					double step = d_wall / sqrt(dot3(f->ed, f->ed));
-					f->ec.x = f->ec.x + step * f->ed.x;
-					f->ec.y = f->ec.y + step * f->ed.y;
-					f->ec.z = f->ec.z + step * f->ed.z;
-					ret = 1;
-					glass_start = true;
-					if (wall_trace == 3)
-						lk_append(c, out, 0, f->ec, f->ed, f->ev, f->irefl, f->w);
-					if (wall_trace == 2)
-						lk_append(c, out, 1, f->ec, f->ed, f->ev, f->irefl, f->w);
-					if (wall_trace == 1) {
-						f->dtrav = f->dtrav + d_wall;
-						if (c.n_shells == 0.) {
-							f->A = 0; f->B = 0;
-						} else {
-							f->A = (2. * (double)q_cntr + (double)r_cntr) * PCB_COSPI_6;
-							f->B = (double)r_cntr * (3. / 2);
-						}
-						f->ix = lk_z_index_incl(c, f->ec.z);
-						f->it = 0;
-						f->it_end = nm;
-						state = S_TRACE_LOOP;
-					} else {
-						state = S_FINISH;
-					}
-				}
-			}
-		} else {
-			f->it = 0;
-			f->it_end = nm;
-			state = S_TRACE_LOOP;
-		}
-	}
-
-	while (state != S_FINISH) {
-		f = &fr[sp];
-		if (state == S_TRACE_LOOP) {
-			if (f->it > f->it_end) { /* loop exhausted with iesc == 1 */
-				esc = f->last_esc;
-				state = S_FRAME_DONE;
-				continue;
-			}
-			f->it++;
-			int r = lk_trace_to_hit(c, *f);
-			if (r != 1) {
-				f->last_esc = r;
-				esc = r;
-				state = S_FRAME_DONE;
-				continue;
-			}
-			f->cont = CONT_TRACE;
-			refl_normal = f->sn;
-			state = S_REFLECT;
-		} else if (state == S_REFLECT) {
-			/* ---- polycap_capil_reflect with leak_calc, capil.c:565-891 ---- */
-			n_refl_events++;
-			V3 sn = refl_normal;
-			norm3(sn);
-			norm3(f->ed);
-			double alfa = dot3(f->ed, sn);
-			if (alfa < 0.) {
-				riesc = -1;
-				state = S_AFTER_REFLECT;
-				continue;
-			}
-			double d_wall = 0;
-			int r_cntr = 0, q_cntr = 0;
-			int wall_trace = lk_trace_wall(c, f->ec, f->ed, d_wall, r_cntr, q_cntr, n_wall_steps);
-			if (wall_trace <= 0) {
-				riesc = -1;
-				state = S_AFTER_REFLECT;
-				continue;
-			}
-			if (sp + 1 >= out.depth) {
-				if (lk_grow(c, out, fr, arena, sp)) {
-					f = &fr[sp];
-				} else {
-					out.err |= LK_ERR_DEPTH;
-					riesc = -1;
-					state = S_AFTER_REFLECT;
-					continue;
-				}
-			}
-			double *w_leak = arena + (size_t)(sp + 1) * nE;
-			ReflGeom g;
-			refl_geometry(sn, f->ed, f->ev, g);
-			bool leak_flag = false, weight_flag = false, bad = false;
-			for (int e = 0; e < nE; e++) {
-				double cons1 = c.ec[EC_KR * nE + e] * alfa * c.sig_rough;
-				double r_rough = exp(-1. * cons1 * cons1);
-				double rtot = fresnel_rtot(c.ec[EC_NRE * nE + e], c.ec[EC_NIM * nE + e], c.ec[EC_I2RE * nE + e], c.ec[EC_I2IM * nE + e], g.cos_t,
-							   g.sin_t, g.frac_s, g.frac_p);
-				if (rtot < 0. || rtot > 1.) {
-					bad = true;
-					break;
-				}
-				w_leak[e] = (1. - rtot * r_rough) * f->w[e] * exp(-1. * d_wall * c.ec[EC_AMU * nE + e]);
-				if (w_leak[e] >= 1.e-4)
-					leak_flag = true;
-				f->w[e] = f->w[e] * rtot * r_rough;
-				if (f->w[e] >= 1.e-4)
-					weight_flag = true;
-			}
-			if (bad) {
-				riesc = -1;
-				state = S_AFTER_REFLECT;
-				continue;
-			}
-			f->ev = g.new_ev;
-			riesc = weight_flag ? 1 : 0;
-			if (leak_flag) {
-				double step = d_wall / sqrt(dot3(f->ed, f->ed));
-				V3 lc = {f->ec.x + step * f->ed.x, f->ec.y + step * f->ed.y, f->ec.z + step * f->ed.z};
-				if (wall_trace == 1) {
-					int zi = lk_z_index(c, lc.z);
-					double eh = ((c.ext[zi + 1] - c.ext[zi]) / (c.z[zi + 1] - c.z[zi])) * (lc.z - c.z[zi]) + c.ext[zi];
-					if (c.n_shells == 0.) {
-						if (sqrt(lc.x * lc.x + lc.y * lc.y) >= eh)
-							wall_trace = 3;
-					} else if (within_pc(eh, lc.x, lc.y) == 0) {
-						wall_trace = 3;
-					}
-				}
-				if (wall_trace == 3)
-					lk_append(c, out, 0, lc, f->ed, f->ev, f->irefl, w_leak);
-				if (wall_trace == 2)
-					lk_append(c, out, 1, lc, f->ed, f->ev, f->irefl, w_leak);
-				if (wall_trace == 1 && lc.z < c.z[nm]) {
-					/* the transmitted part continues as a secondary photon in capillary (q_cntr, r_cntr): capil.c:711-886 */
-					f->iesc_after = riesc;
-					f->rec_mark = out.nrec;
-					LkFrame *s = &fr[sp + 1];
-					s->ec = lc;
-					s->ed = f->ed;
-					s->ev = f->ev;
-					s->irefl = f->irefl;
-					s->dtrav = f->dtrav + d_wall;
-					s->w = w_leak;
-					if (c.n_shells == 0.) {
-						s->A = 0; s->B = 0;
-					} else {
-						s->A = (2. * (double)q_cntr + (double)r_cntr) * PCB_COSPI_6;
-						s->B = (double)r_cntr * (3. / 2);
-					}
-					s->ix = lk_z_index_incl(c, lc.z);
-					s->it = s->ix;
-					s->it_end = nm;
-					s->last_esc = 0;
-					s->cont = CONT_TRACE;
-					sp++;
-					state = S_TRACE_LOOP;
-					continue;
-				}
-			}
-			state = S_AFTER_REFLECT;
-		} else if (state == S_FRAME_DONE) {
-			if (sp == 0) {
-				unit_ret = esc; /* single polycap_capil_trace that found no reflection: -1 / -2 / -3 */
-				state = S_FINISH;
-				continue;
-			}
-			LkFrame *s = &fr[sp];
-			sp--;
-			f = &fr[sp];
-			if (esc == -1 || esc == -3) { /* capil.c:799-805: the secondary's leaks are dropped, reflect returns -2 */
-				out.nrec = f->rec_mark;
-				riesc = -2;
-			} else {
-				if (esc == 1 || esc == -2) { /* the secondary reached the end: its weights leave as one more leak, capil.c:845-880 */
-					double tt = ((c.z[nm] - s->ec.z) / s->ed.z);
-					V3 e3 = {s->ec.x + s->ed.x * tt, s->ec.y + s->ed.y * tt, s->ec.z + s->ed.z * tt};
-					int inside = within_pc(c.ext[nm], e3.x, e3.y);
-					if (inside == 0)
-						lk_append(c, out, 0, e3, f->ed, f->ev, f->irefl, s->w);
-					else if (inside == 1)
-						lk_append(c, out, 1, e3, f->ed, f->ev, f->irefl, s->w);
-				}
-				riesc = f->iesc_after;
-			}
-			state = S_AFTER_REFLECT;
-		} else { /* S_AFTER_REFLECT */
-			if (f->cont == CONT_FACE) { /* photon.c:652: return value of the entrance-face reflect is ignored */
-				state = S_FINISH;
-				continue;
-			}
-			if (f->cont == CONT_UNIT) { /* single polycap_capil_reflect: its return value is the result */
-				unit_ret = riesc;
-				state = S_FINISH;
-				continue;
-			}
-			if (riesc == 1) { /* capil.c:1346-1352 */
-				f->ed.x = f->ed.x - 2.0 * f->cosalfa * f->sn.x;
-				f->ed.y = f->ed.y - 2.0 * f->cosalfa * f->sn.y;
-				f->ed.z = f->ed.z - 2.0 * f->cosalfa * f->sn.z;
-				norm3(f->ed);
-				f->irefl++;
-				esc = 1;
-			} else if (riesc == -1 || riesc == -2) {
-				esc = -1;
-			} else {
-				esc = riesc;
-			}
-			f->last_esc = esc;
-			state = (esc == 1) ? S_TRACE_LOOP : S_FRAME_DONE;
-			if (unit && sp == 0) { /* single polycap_capil_trace: one wall hit of the primary, reflected */
-				unit_ret = esc;
-				state = S_FINISH;
-			}
-		}
-	}
-
-	f = &fr[0];
-	if (!finished && ret != 2 && ret != -1 && !glass_start) { /* photon.c:947-954 */
-		esc = f->last_esc;
-		if (esc == -1 || esc == -3)
-			ret = -1;
-		else
-			ret = (esc == 0) ? 0 : 1;
-	} else if (glass_start && ret == 1) {
-		esc = f->last_esc;
-		bool traced = (f->it > 0);
-		if (traced && (esc == -1 || esc == -3)) {
-			ret = -1;
-		} else {
-			if (traced && (esc == 1 || esc == -2)) { /* photon.c:829-854 */
-				double tt = ((c.z[nm] - f->ec.z) / f->ed.z);
-				f->ec.x = f->ec.x + f->ed.x * tt;
-				f->ec.y = f->ec.y + f->ed.y * tt;
-				f->ec.z = f->ec.z + f->ed.z * tt;
-				int inside = within_pc(c.ext[nm], f->ec.x, f->ec.y);
-				if (inside == 0)
-					lk_append(c, out, 0, f->ec, f->ed, f->ev, f->irefl, f->w);
-				else if (inside == 1)
-					lk_append(c, out, 1, f->ec, f->ed, f->ev, f->irefl, f->w);
-			}
-			for (int e = 0; e < nE; e++) /* photon.c:856-885 */
-				f->w[e] = 0.;
-			f->ec.x = c.ext[nm] + 1.;
-			f->ec.y = c.ext[nm] + 1.;
-			f->ec.z = c.z[nm];
-			f->ed = start_dir;
-			norm3(f->ed);
-		}
-	}
-	if (unit)
-		ret = unit_ret;
-	res.ret = ret;
-	res.ec = f->ec;
-	res.ed = f->ed;
-	res.ev = f->ev;
-	res.irefl = f->irefl;
-	res.dtrav = f->dtrav;
-}
+#define LK_WARPS (LK_THREADS / 32)
+#ifndef LK_BLOCKS_PER_SM
+#define LK_BLOCKS_PER_SM 1 /* registers as the code needs them: capping them at 128 (4 blocks, 16 warps per SM) measured 2.6x slower per warp */
+#endif
 
 /* ------------------------------------------------------------------ kernels */
 
@@ -876,9 +42,9 @@ struct LkParams {
 	unsigned long long n_todo;
 	unsigned long long *retry;      /* first launch: ids whose nesting depth / record count exceeded the small capacities ... */
 	unsigned long long *n_retry;    /* ... and how many */
-	double *arena;            /* [threads][(depth+1)*nE] */
-	LkFrame *frames;          /* [threads][depth] */
-	double *rec;              /* [threads][rec_cap*(11+nE)] scratch strips */
+	double *arena;            /* [warps][(depth+1)*nE] */
+	LkFrame *frames;          /* [warps][depth] */
+	double *rec;              /* [warps][rec_cap*(11+nE)] scratch strips */
 	LkFrame *big_frames;      /* pool of full-size workspaces for the photons that outgrow the small ones (first launch) */
 	double *big_arena, *big_rec;
 	unsigned long long *big_next, big_n;
@@ -896,19 +62,20 @@ struct LkParams {
 	int *err;
 };
 
-__global__ void __launch_bounds__(LK_THREADS) pcb_leak_kernel(const LkParams P)
+__global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(const LkParams P)
 {
 	const LkCtx &c = P.c;
 	const int nE = c.nE;
-	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	double *const arena0 = P.arena + tid * (unsigned long long)(P.depth + 1) * nE;
-	LkFrame *const frames0 = P.frames + tid * (unsigned long long)P.depth;
-	double *const rec0 = P.rec + tid * (unsigned long long)P.rec_cap * (11 + nE);
+	const int lane = lk_lane();
+	const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	double *const arena0 = P.arena + wid * (unsigned long long)(P.depth + 1) * nE;
+	LkFrame *const frames0 = P.frames + wid * (unsigned long long)P.depth;
+	double *const rec0 = P.rec + wid * (unsigned long long)P.rec_cap * (11 + nE);
 	LkOut out;
 	out.big_frames = P.big_frames; out.big_arena = P.big_arena; out.big_rec = P.big_rec; out.big_next = P.big_next; out.big_n = P.big_n;
-	unsigned long long refl_events = 0, wall_steps = 0;
+	LkWork total{};
 	for (;;) {
-		unsigned long long i = atomicAdd(P.next, 1ULL);
+		unsigned long long i = lk_fetch_add(P.next, 1ULL);
 		if (P.todo) {
 			if (i >= P.n_todo)
 				break;
@@ -928,104 +95,134 @@ __global__ void __launch_bounds__(LK_THREADS) pcb_leak_kernel(const LkParams P)
 		}
 		out.nrec = 0;
 		out.err = 0;
-		out.rec = rec0; /* every photon starts in the thread's own (small) workspace */
+		out.rec = rec0; /* every photon starts in the warp's own (small) workspace */
 		out.cap = P.rec_cap;
 		out.depth = P.depth;
 		double *arena = arena0;
 		LkFrame *frames = frames0;
 		LkResult r;
-		unsigned long long ev_photon = 0, steps_photon = 0;
-		lk_photon(c, s0.coords, s0.dir, s0.ev, 0.0, frames, arena, out, r, ev_photon, steps_photon);
+		LkWork wk{};
+		lk_sync(); /* the previous photon's copy-out has read this workspace across lanes */
+		lk_photon(c, s0.coords, s0.dir, s0.ev, 0.0, frames, arena, out, r, wk);
 		if (out.err) {
-			if (P.retry) { /* did not fit the small per-thread capacities: the second launch redoes this id with the full ones */
-				P.retry[atomicAdd(P.n_retry, 1ULL)] = i;
-				P.leak_n[i] = 0;
-				P.leak_off[i] = 0;
+			if (P.retry) { /* did not fit the small per-warp capacities: the second launch redoes this id with the full ones */
+				const unsigned long long slot = lk_fetch_add(P.n_retry, 1ULL);
+				if (lane == 0) {
+					P.retry[slot] = i;
+					P.leak_n[i] = 0;
+					P.leak_off[i] = 0;
+				}
 				continue;
 			}
-			atomicOr(P.err, out.err);
+			if (lane == 0)
+				atomicOr(P.err, out.err);
 		}
-		refl_events += ev_photon;
-		wall_steps += steps_photon;
+		total.refl_events += wk.refl_events;
+		total.wall_steps += wk.wall_steps;
+		total.wall_evals += wk.wall_evals;
+		total.scan_rounds += wk.scan_rounds;
+#ifdef LK_PROFILE
+		total.t_total += wk.t_total; total.t_wall += wk.t_wall; total.t_jump += wk.t_jump; total.t_scan += wk.t_scan; total.t_energy += wk.t_energy;
+		total.n_jump_try += wk.n_jump_try;
+#endif
 		int status = r.ret;
 		const double zt = c.z[c.nmax];
 		if (P.mode == 0 && r.ret == 1) { /* exit-window test, source.c:762-777 */
 			double px = r.ec.x + r.ed.x * (zt - r.ec.z) / r.ed.z;
 			double py = r.ec.y + r.ed.y * (zt - r.ec.z) / r.ed.z;
-			int inside = c.mono ? ((sqrt(px * px + py * py) > c.ext[c.nmax]) ? 0 : 1) : within_pc(c.ext[c.nmax], px, py);
+			int inside = c.mono ? ((sqrt(px * px + py * py) > c.ext[c.nmax]) ? 0 : 1) : lk_within_pc(c.ext[c.nmax], px, py);
 			if (inside != 1)
 				status = ST_MISSED_WINDOW;
 		}
-		P.status[i] = (int8_t)status;
-		P.irefl[i] = (int)r.irefl;
 		double *F = P.fields;
 		const unsigned long long n = P.n;
-		if (P.mode != 0) {
-			F[0 * n + i] = r.ec.x; F[1 * n + i] = r.ec.y; F[2 * n + i] = r.ec.z;
-			F[3 * n + i] = r.ed.x; F[4 * n + i] = r.ed.y; F[5 * n + i] = r.ed.z;
-			F[6 * n + i] = r.ev.x; F[7 * n + i] = r.ev.y; F[8 * n + i] = r.ev.z;
-			F[9 * n + i] = r.dtrav;
-			F[10 * n + i] = 0;
-		} else if (status == ST_EXIT) { /* record of source.c:779-798, 893-923 */
-			V3 sd = s0.dir;
-			norm3(sd);
-			norm3(sd);
-			F[0 * n + i] = s0.src_x; F[1 * n + i] = s0.src_y;
-			F[2 * n + i] = s0.coords.x; F[3 * n + i] = s0.coords.y;
-			F[4 * n + i] = sd.x; F[5 * n + i] = sd.y;
-			double ca = dot3(s0.ev, sd);
-			double al = acos(ca);
-			double c_ae = 1. / sin(al), c_be = -1. * c_ae * ca;
-			V3 t = {s0.ev.x * c_ae + sd.x * c_be, s0.ev.y * c_ae + sd.y * c_be, s0.ev.z * c_ae + sd.z * c_be};
-			norm3(t);
-			F[6 * n + i] = round(t.x); F[7 * n + i] = round(t.y);
-			double px = r.ec.x + r.ed.x * (zt - r.ec.z) / r.ed.z;
-			double py = r.ec.y + r.ed.y * (zt - r.ec.z) / r.ed.z;
-			double pz = r.ec.z + r.ed.z * (zt - r.ec.z) / r.ed.z;
-			F[8 * n + i] = px; F[9 * n + i] = py; F[10 * n + i] = pz;
-			F[11 * n + i] = r.ed.x; F[12 * n + i] = r.ed.y;
-			V3 u = {r.ev.x * c_ae + r.ed.x * c_be, r.ev.y * c_ae + r.ed.y * c_be, r.ev.z * c_ae + r.ed.z * c_be};
-			norm3(u);
-			F[13 * n + i] = round(u.x); F[14 * n + i] = round(u.y);
-			F[15 * n + i] = (double)r.irefl;
-			F[16 * n + i] = r.dtrav + sqrt((px - r.ec.x) * (px - r.ec.x) + (py - r.ec.y) * (py - r.ec.y) + (zt - r.ec.z) * (zt - r.ec.z));
+		if (lane == 0) {
+			P.status[i] = (int8_t)status;
+			P.irefl[i] = (int)r.irefl;
+			if (P.mode != 0) {
+				F[0 * n + i] = r.ec.x; F[1 * n + i] = r.ec.y; F[2 * n + i] = r.ec.z;
+				F[3 * n + i] = r.ed.x; F[4 * n + i] = r.ed.y; F[5 * n + i] = r.ed.z;
+				F[6 * n + i] = r.ev.x; F[7 * n + i] = r.ev.y; F[8 * n + i] = r.ev.z;
+				F[9 * n + i] = r.dtrav;
+				F[10 * n + i] = 0;
+			} else if (status == ST_EXIT) { /* record of source.c:779-798, 893-923 */
+				V3 sd = s0.dir;
+				norm3(sd);
+				norm3(sd);
+				F[0 * n + i] = s0.src_x; F[1 * n + i] = s0.src_y;
+				F[2 * n + i] = s0.coords.x; F[3 * n + i] = s0.coords.y;
+				F[4 * n + i] = sd.x; F[5 * n + i] = sd.y;
+				double ca = dot3(s0.ev, sd);
+				double al = acos(ca);
+				double c_ae = 1. / sin(al), c_be = -1. * c_ae * ca;
+				V3 t = {s0.ev.x * c_ae + sd.x * c_be, s0.ev.y * c_ae + sd.y * c_be, s0.ev.z * c_ae + sd.z * c_be};
+				norm3(t);
+				F[6 * n + i] = round(t.x); F[7 * n + i] = round(t.y);
+				double px = r.ec.x + r.ed.x * (zt - r.ec.z) / r.ed.z;
+				double py = r.ec.y + r.ed.y * (zt - r.ec.z) / r.ed.z;
+				double pz = r.ec.z + r.ed.z * (zt - r.ec.z) / r.ed.z;
+				F[8 * n + i] = px; F[9 * n + i] = py; F[10 * n + i] = pz;
+				F[11 * n + i] = r.ed.x; F[12 * n + i] = r.ed.y;
+				V3 u = {r.ev.x * c_ae + r.ed.x * c_be, r.ev.y * c_ae + r.ed.y * c_be, r.ev.z * c_ae + r.ed.z * c_be};
+				norm3(u);
+				F[13 * n + i] = round(u.x); F[14 * n + i] = round(u.y);
+				F[15 * n + i] = (double)r.irefl;
+				F[16 * n + i] = r.dtrav + sqrt((px - r.ec.x) * (px - r.ec.x) + (py - r.ec.y) * (py - r.ec.y) + (zt - r.ec.z) * (zt - r.ec.z));
+			}
 		}
-		for (int e = 0; e < nE; e++)
+		for (int e = lane; e < nE; e += 32)
 			P.weights[i * nE + e] = arena[e];
 		/* leak records of this id -> pool (the reference keeps the leaks of photons with codes 1, 0, 2; source.c:799-879) */
 		int keep = out.nrec;
 		if (P.mode == 0 && (status == ST_OUTSIDE || status == ST_ERROR))
 			keep = 0;
-		P.leak_n[i] = keep;
 		if (keep > 0) {
-			unsigned long long off = atomicAdd(P.leak_pool_used, (unsigned long long)keep);
-			P.leak_off[i] = off;
+			const unsigned long long off = lk_fetch_add(P.leak_pool_used, (unsigned long long)keep);
 			if (off + keep <= P.leak_pool_cap) {
 				const size_t stride = 11 + nE;
-				for (size_t k = 0; k < (size_t)keep * stride; k++)
+				for (size_t k = lane; k < (size_t)keep * stride; k += 32)
 					P.leak_pool[off * stride + k] = out.rec[k];
-			} else {
+			} else if (lane == 0) {
 				atomicOr(P.err, LK_ERR_POOL);
 			}
-		} else {
+			if (lane == 0)
+				P.leak_off[i] = off;
+		} else if (lane == 0) {
 			P.leak_off[i] = 0;
 		}
+		if (lane == 0)
+			P.leak_n[i] = keep;
 	}
-	atomicAdd(P.refl_events, refl_events);
-	atomicAdd(P.refl_events + 1, wall_steps);
+	if (lane == 0) {
+		atomicAdd(P.refl_events, total.refl_events);
+		atomicAdd(P.refl_events + 1, total.wall_steps);
+		atomicAdd(P.refl_events + 2, total.wall_evals);
+		atomicAdd(P.refl_events + 3, total.scan_rounds);
+#ifdef LK_PROFILE
+		atomicAdd(P.refl_events + 4, total.t_total);
+		atomicAdd(P.refl_events + 5, total.t_wall);
+		atomicAdd(P.refl_events + 6, total.t_jump);
+		atomicAdd(P.refl_events + 7, total.t_scan);
+		atomicAdd(P.refl_events + 8, total.t_energy);
+		atomicAdd(P.refl_events + 9, total.n_jump_try);
+#endif
+	}
 }
 
-/* single-item kernels for the reference's private test entry points */
+/* single-item kernels for the reference's private test entry points (one warp) */
 __global__ void lk_unit_trace_wall_kernel(LkCtx c, const double *in, double *outd, int *outi)
 {
 	V3 ec = {in[0], in[1], in[2]}, ed = {in[3], in[4], in[5]};
 	double d_travel;
 	int r_cntr, q_cntr;
-	unsigned long long steps = 0;
-	outi[0] = lk_trace_wall(c, ec, ed, d_travel, r_cntr, q_cntr, steps);
-	outi[1] = r_cntr;
-	outi[2] = q_cntr;
-	outd[0] = d_travel;
+	LkWork wk{};
+	const int rc = lk_trace_wall(c, ec, ed, d_travel, r_cntr, q_cntr, wk);
+	if (lk_lane() == 0) {
+		outi[0] = rc;
+		outi[1] = r_cntr;
+		outi[2] = q_cntr;
+		outd[0] = d_travel;
+	}
 }
 
 /* single polycap_capil_reflect / polycap_capil_trace with leak_calc = true on one photon state:
@@ -1033,10 +230,11 @@ __global__ void lk_unit_trace_wall_kernel(LkCtx c, const double *in, double *out
 __global__ void lk_unit_step_kernel(LkCtx c, int mode, const double *in, int ix, double *w, LkFrame *frames, double *arena, double *rec, int rec_cap, int depth,
 				    double *outs, int *nrec_out, int *err_out)
 {
+	const int lane = lk_lane();
 	LkOut out;
 	out.rec = rec; out.nrec = 0; out.err = 0; out.cap = rec_cap; out.depth = depth;
 	out.big_frames = nullptr; out.big_arena = nullptr; out.big_rec = nullptr; out.big_next = nullptr; out.big_n = 0;
-	for (int e = 0; e < c.nE; e++)
+	for (int e = lane; e < c.nE; e += 32) /* lane-wise, like every weight vector of the state machine */
 		arena[e] = w[e];
 	LkUnit u;
 	u.mode = mode;
@@ -1046,21 +244,23 @@ __global__ void lk_unit_step_kernel(LkCtx c, int mode, const double *in, int ix,
 	u.ix = ix;
 	V3 sc = {in[0], in[1], in[2]}, sd = {in[3], in[4], in[5]}, sev = {in[6], in[7], in[8]};
 	LkResult r;
-	unsigned long long ev = 0, steps = 0;
+	LkWork wk{};
 	LkFrame *fr = frames;
 	double *ar = arena;
-	lk_photon(c, sc, sd, sev, in[13], fr, ar, out, r, ev, steps, &u);
-	for (int e = 0; e < c.nE; e++)
+	lk_photon(c, sc, sd, sev, in[13], fr, ar, out, r, wk, &u);
+	for (int e = lane; e < c.nE; e += 32)
 		w[e] = ar[e];
-	outs[0] = (double)r.ret;
-	outs[1] = r.ec.x; outs[2] = r.ec.y; outs[3] = r.ec.z;
-	outs[4] = r.ed.x; outs[5] = r.ed.y; outs[6] = r.ed.z;
-	outs[7] = r.ev.x; outs[8] = r.ev.y; outs[9] = r.ev.z;
-	outs[10] = (double)r.irefl;
-	outs[11] = r.dtrav;
-	outs[12] = (double)fr[0].ix;
-	*nrec_out = out.nrec;
-	*err_out = out.err;
+	if (lane == 0) {
+		outs[0] = (double)r.ret;
+		outs[1] = r.ec.x; outs[2] = r.ec.y; outs[3] = r.ec.z;
+		outs[4] = r.ed.x; outs[5] = r.ed.y; outs[6] = r.ed.z;
+		outs[7] = r.ev.x; outs[8] = r.ev.y; outs[9] = r.ev.z;
+		outs[10] = (double)r.irefl;
+		outs[11] = r.dtrav;
+		outs[12] = (double)fr[0].ix;
+		*nrec_out = out.nrec;
+		*err_out = out.err;
+	}
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -1100,7 +300,7 @@ struct DevMem {
 /* shared driver: runs n photons (ids or replay states), fills host outputs */
 extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src, uint64_t seed, int64_t id0, int64_t n, const double *coords,
 			    const double *dir, const double *ev, int8_t *status, int *irefl, double *fields /* [F][n] field-major */, double *weights,
-			    int *leak_n, double **leak_rec, int64_t *n_leak_rec, int64_t *work /* [2]: capil_reflect events, wall-march steps */)
+			    int *leak_n, double **leak_rec, int64_t *n_leak_rec, int64_t *work /* [4]: capil_reflect events, wall-march steps, steps evaluated, scan rounds */)
 {
 	const int nE = o->nE;
 	const int mode = src ? 0 : 1;
@@ -1112,6 +312,7 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	P.c.mono = o->mono;
 	P.c.monotonic = o->monotonic;
 	P.c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
+	P.c.no_jump = getenv("POLYCAP_B200_LEAK_NO_JUMP") ? 1 : 0;
 	P.c.n_shells = o->n_shells;
 	P.c.sig_rough = o->sig_rough;
 	P.c.z = o->d_z; P.c.cap = o->d_cap; P.c.ext = o->d_ext; P.c.hexz = o->d_hexz; P.c.ec = o->d_ec;
@@ -1123,30 +324,34 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	P.mode = mode;
 	P.id0 = (unsigned long long)id0;
 	P.n = (unsigned long long)n;
-	/* Per-thread workspace: frame stack, weight arena, record strip; the thread count follows from a memory budget.  Few photons
+	/* Per-warp workspace: frame stack, weight arena, record strip; the warp count follows from a memory budget.  Few photons
 	 * nest deeper than a few dozen secondaries, but one that does needs LK_DEPTH frames and LK_REC_CAP records, i.e. megabytes per
-	 * thread at long energy grids -- so the first launch gives every thread small capacities (many threads), collects the ids that
-	 * did not fit, and a second launch redoes only those with the full capacities (few threads). */
+	 * warp at long energy grids -- so every warp starts with small capacities, a photon that outgrows them moves to a full-size
+	 * workspace from a pool, and the ids that found the pool empty are redone by a second launch with full capacities (few warps). */
 	const size_t stride = 11 + (size_t)nE;
-	auto per_thread_bytes = [&](int depth, int rcap) { return (size_t)depth * sizeof(LkFrame) + (size_t)(depth + 1) * nE * 8 + (size_t)rcap * stride * 8; };
-	const int depth1 = getenv("POLYCAP_B200_LEAK_DEPTH1") ? atoi(getenv("POLYCAP_B200_LEAK_DEPTH1")) : 48;
+	auto per_warp_bytes = [&](int depth, int rcap) { return (size_t)depth * sizeof(LkFrame) + (size_t)(depth + 1) * nE * 8 + (size_t)rcap * stride * 8; };
+	const int depth1 = getenv("POLYCAP_B200_LEAK_DEPTH1") ? atoi(getenv("POLYCAP_B200_LEAK_DEPTH1")) : 96;
 	const int rcap1 = 4 * depth1;
 	size_t free_b = 0, total_b = 0;
 	LCK(cudaMemGetInfo(&free_b, &total_b));
 	size_t budget = free_b / 3;
 	if (budget > ((size_t)24 << 30))
 		budget = (size_t)24 << 30;
+	int per_sm = 0; /* resident blocks per SM: the persistent warps of a launch are exactly the ones the device holds at once */
+	LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcb_leak_kernel, LK_THREADS, 0));
+	if (per_sm < 1)
+		per_sm = 1;
 	auto blocks_for = [&](int64_t items, int depth, int rcap) {
-		int blocks = (int)((items + LK_THREADS - 1) / LK_THREADS);
-		int max_blocks = (int)(budget / (per_thread_bytes(depth, rcap) * LK_THREADS));
-		if (max_blocks > o->sm_count * 4)
-			max_blocks = o->sm_count * 4;
+		int blocks = (int)((items + LK_WARPS - 1) / LK_WARPS);
+		int max_blocks = (int)(budget / (per_warp_bytes(depth, rcap) * LK_WARPS));
+		if (max_blocks > o->sm_count * per_sm)
+			max_blocks = o->sm_count * per_sm;
 		if (max_blocks < 1)
 			max_blocks = 1;
 		return blocks > max_blocks ? max_blocks : blocks;
 	};
 	int blocks = blocks_for(n, depth1, rcap1);
-	size_t threads = (size_t)blocks * LK_THREADS;
+	size_t warps = (size_t)blocks * LK_WARPS;
 	double *d_rin = nullptr;
 	P.depth = depth1;
 	P.rec_cap = rcap1;
@@ -1154,20 +359,22 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	LCK(M.alloc(&P.retry, (size_t)n * 8));
 	LCK(M.alloc(&P.n_retry, 8));
 	LCK(cudaMemset(P.n_retry, 0, 8));
-	LCK(M.alloc(&P.arena, threads * (size_t)(depth1 + 1) * nE * 8));
-	LCK(M.alloc(&P.frames, threads * (size_t)depth1 * sizeof(LkFrame)));
-	LCK(M.alloc(&P.rec, threads * (size_t)rcap1 * stride * 8));
+	LCK(M.alloc(&P.arena, warps * (size_t)(depth1 + 1) * nE * 8));
+	LCK(M.alloc(&P.frames, warps * (size_t)depth1 * sizeof(LkFrame)));
+	LCK(M.alloc(&P.rec, warps * (size_t)rcap1 * stride * 8));
 	{ /* full-size workspaces for the deep photons of this launch: a quarter of what is left, at most 16 GB, at most one per id */
 		size_t fb = 0, tb = 0;
 		LCK(cudaMemGetInfo(&fb, &tb));
 		size_t big_budget = fb / 4;
 		if (big_budget > ((size_t)16 << 30))
 			big_budget = (size_t)16 << 30;
-		unsigned long long nb = big_budget / per_thread_bytes(LK_DEPTH, LK_REC_CAP);
+		unsigned long long nb = big_budget / per_warp_bytes(LK_DEPTH, LK_REC_CAP);
 		if (nb > (unsigned long long)n)
 			nb = (unsigned long long)n;
-		if (nb > 4096)
-			nb = 4096;
+		const char *bm = getenv("POLYCAP_B200_LEAK_BIG_MAX"); /* profiling aid: fewer full-size workspaces = less memory for ncu to save and restore */
+		const unsigned long long nb_max = bm ? (unsigned long long)atoll(bm) : 4096ULL;
+		if (nb > nb_max)
+			nb = nb_max;
 		P.big_n = nb;
 		LCK(M.alloc(&P.big_next, 8));
 		LCK(cudaMemset(P.big_next, 0, 8));
@@ -1181,9 +388,10 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	LCK(M.alloc(&P.weights, (size_t)n * nE * 8));
 	LCK(M.alloc(&P.leak_n, (size_t)n * 4));
 	LCK(M.alloc(&P.leak_off, (size_t)n * 8));
-	/* record pool of the wave: 24 leaks per id on average, within a third of the free memory; a wave that overflows it is
-	 * reported with return code -2 and retried by the caller with fewer ids (the reference simply reallocs per photon) */
-	P.leak_pool_cap = (unsigned long long)n * 24 + 65536;
+	/* record pool of the wave: room for 96 leaks per id on average (the 1-40 keV ellipsoidal run leaves 39), within a third of the
+	 * free memory; a wave that overflows it is reported with return code -2 and retried by the caller with fewer ids (the reference
+	 * simply reallocs per photon) */
+	P.leak_pool_cap = (unsigned long long)n * 96 + 65536;
 	{
 		const unsigned long long fit = (unsigned long long)(free_b / 3) / (stride * 8);
 		if (P.leak_pool_cap > fit)
@@ -1191,11 +399,11 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	}
 	LCK(M.alloc(&P.leak_pool, (size_t)P.leak_pool_cap * stride * 8));
 	LCK(M.alloc(&P.leak_pool_used, 8));
-	LCK(M.alloc(&P.refl_events, 16));
+	LCK(M.alloc(&P.refl_events, 128));
 	LCK(M.alloc(&P.err, 4));
 	LCK(cudaMemset(P.next, 0, 8));
 	LCK(cudaMemset(P.leak_pool_used, 0, 8));
-	LCK(cudaMemset(P.refl_events, 0, 16));
+	LCK(cudaMemset(P.refl_events, 0, 128));
 	LCK(cudaMemset(P.err, 0, 4));
 	if (mode == 1) {
 		LCK(M.alloc(&d_rin, (size_t)n * 9 * 8));
@@ -1204,9 +412,16 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 		LCK(cudaMemcpy(d_rin + 6 * n, ev, (size_t)n * 24, cudaMemcpyHostToDevice));
 		P.rin = d_rin;
 	}
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float kernel_ms = 0, kernel2_ms = 0;
+	LCK(cudaEventCreate(&ev0));
+	LCK(cudaEventCreate(&ev1));
+	LCK(cudaEventRecord(ev0));
 	pcb_leak_kernel<<<blocks, LK_THREADS>>>(P);
 	LCK(cudaGetLastError());
+	LCK(cudaEventRecord(ev1));
 	LCK(cudaDeviceSynchronize());
+	cudaEventElapsedTime(&kernel_ms, ev0, ev1);
 	unsigned long long n_retry = 0;
 	LCK(cudaMemcpy(&n_retry, P.n_retry, 8, cudaMemcpyDeviceToHost));
 	if (n_retry > 0) { /* second launch: the deep photons with the full capacities */
@@ -1221,27 +436,42 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 		Q.big_next = nullptr;
 		Q.big_n = 0;
 		const int blocks2 = blocks_for((int64_t)n_retry, LK_DEPTH, LK_REC_CAP);
-		const size_t threads2 = (size_t)blocks2 * LK_THREADS;
-		LCK(M2.alloc(&Q.arena, threads2 * (size_t)(LK_DEPTH + 1) * nE * 8));
-		LCK(M2.alloc(&Q.frames, threads2 * (size_t)LK_DEPTH * sizeof(LkFrame)));
-		LCK(M2.alloc(&Q.rec, threads2 * (size_t)LK_REC_CAP * stride * 8));
+		const size_t warps2 = (size_t)blocks2 * LK_WARPS;
+		LCK(M2.alloc(&Q.arena, warps2 * (size_t)(LK_DEPTH + 1) * nE * 8));
+		LCK(M2.alloc(&Q.frames, warps2 * (size_t)LK_DEPTH * sizeof(LkFrame)));
+		LCK(M2.alloc(&Q.rec, warps2 * (size_t)LK_REC_CAP * stride * 8));
 		LCK(cudaMemset(Q.next, 0, 8));
+		LCK(cudaEventRecord(ev0));
 		pcb_leak_kernel<<<blocks2, LK_THREADS>>>(Q);
 		LCK(cudaGetLastError());
+		LCK(cudaEventRecord(ev1));
 		LCK(cudaDeviceSynchronize());
+		cudaEventElapsedTime(&kernel2_ms, ev0, ev1);
 	}
 	if (getenv("POLYCAP_B200_PHASES"))
 	{
 		unsigned long long moved = 0;
 		cudaMemcpy(&moved, P.big_next, 8, cudaMemcpyDeviceToHost);
-		fprintf(stderr, "polycap-b200 phases: leak wave of %lld ids: %d x %d threads with %d frames each, %llu photons moved to a full-size workspace (%llu available), "
-				"%llu ids redone in a second launch\n", (long long)n, blocks, LK_THREADS, depth1, moved, P.big_n, n_retry);
+		fprintf(stderr, "polycap-b200 phases: leak wave of %lld ids: %d blocks x %d warps with %d frames each, %llu photons moved to a full-size workspace (%llu available), "
+				"%llu ids redone in a second launch\n", (long long)n, blocks, LK_WARPS, depth1, moved, P.big_n, n_retry);
 	}
+	cudaEventDestroy(ev0);
+	cudaEventDestroy(ev1);
 	int err = 0;
-	unsigned long long used = 0, refl[2] = {0, 0};
+	unsigned long long used = 0, refl[16] = {0};
 	LCK(cudaMemcpy(&err, P.err, 4, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(&used, P.leak_pool_used, 8, cudaMemcpyDeviceToHost));
-	LCK(cudaMemcpy(refl, P.refl_events, 16, cudaMemcpyDeviceToHost));
+	LCK(cudaMemcpy(refl, P.refl_events, 128, cudaMemcpyDeviceToHost));
+	if (getenv("POLYCAP_B200_PHASES")) {
+		fprintf(stderr, "polycap-b200 phases: leak kernel %.1f ms (+ %.1f ms second launch): %llu reflection events, %llu march steps (%llu evaluated), %llu scan rounds\n",
+			kernel_ms, kernel2_ms, refl[0], refl[1], refl[2], refl[3]);
+#ifdef LK_PROFILE
+		const double tt = (double)refl[4] > 0 ? (double)refl[4] : 1.0;
+		fprintf(stderr, "polycap-b200 phases: leak clocks per reflection event (warp-time): total %.0f = wall march %.0f (of which jumps %.0f, %.2f attempts) + segment scan %.0f + energy loop %.0f + rest %.0f\n",
+			tt / (double)refl[0], (double)refl[5] / (double)refl[0], (double)refl[6] / (double)refl[0], (double)refl[9] / (double)refl[0], (double)refl[7] / (double)refl[0],
+			(double)refl[8] / (double)refl[0], (tt - (double)refl[5] - (double)refl[7] - (double)refl[8]) / (double)refl[0]);
+#endif
+	}
 	if (err & (LK_ERR_DEPTH | LK_ERR_RECORDS)) {
 		g_lk_err = (err & LK_ERR_DEPTH) ? "leak transport: more than 1400 nested secondary photons" : "leak transport: more than 2048 leak records from one photon";
 		return -1;
@@ -1251,8 +481,8 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 		return -2;
 	}
 	if (work) {
-		work[0] = (int64_t)refl[0];
-		work[1] = (int64_t)refl[1];
+		for (int k = 0; k < 4; k++)
+			work[k] = (int64_t)refl[k];
 	}
 	LCK(cudaMemcpy(status, P.status, (size_t)n, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(irefl, P.irefl, (size_t)n * 4, cudaMemcpyDeviceToHost));
@@ -1283,6 +513,7 @@ extern "C" int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const doubl
 	LkCtx c{};
 	c.nmax = o->nmax; c.nE = o->nE; c.mono = o->mono; c.monotonic = o->monotonic; c.n_shells = o->n_shells; c.sig_rough = o->sig_rough;
 	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
+	c.no_jump = getenv("POLYCAP_B200_LEAK_NO_JUMP") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
 	const size_t nE = (size_t)o->nE, stride = 11 + nE;
 	*leak_rec = nullptr;
@@ -1300,7 +531,7 @@ extern "C" int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const doubl
 	LCK(M.alloc(&d_i, 8));
 	LCK(cudaMemcpy(d_in, in, 16 * 8, cudaMemcpyHostToDevice));
 	LCK(cudaMemcpy(d_w, weights, nE * 8, cudaMemcpyHostToDevice));
-	lk_unit_step_kernel<<<1, 1>>>(c, mode, d_in, ix, d_w, d_frames, d_arena, d_rec, LK_REC_CAP, LK_DEPTH, d_outs, d_i, d_i + 1);
+	lk_unit_step_kernel<<<1, 32>>>(c, mode, d_in, ix, d_w, d_frames, d_arena, d_rec, LK_REC_CAP, LK_DEPTH, d_outs, d_i, d_i + 1);
 	LCK(cudaGetLastError());
 	int hi[2];
 	LCK(cudaMemcpy(hi, d_i, 8, cudaMemcpyDeviceToHost));
@@ -1324,6 +555,7 @@ extern "C" int pcb_leak_unit_trace_wall(const pcb_leak_optic *o, const double in
 	LkCtx c{};
 	c.nmax = o->nmax; c.nE = o->nE; c.mono = o->mono; c.monotonic = o->monotonic; c.n_shells = o->n_shells; c.sig_rough = o->sig_rough;
 	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
+	c.no_jump = getenv("POLYCAP_B200_LEAK_NO_JUMP") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
 	DevMem M;
 	double *d_in, *d_out;
@@ -1332,7 +564,7 @@ extern "C" int pcb_leak_unit_trace_wall(const pcb_leak_optic *o, const double in
 	LCK(M.alloc(&d_out, 8));
 	LCK(M.alloc(&d_i, 12));
 	LCK(cudaMemcpy(d_in, in, 48, cudaMemcpyHostToDevice));
-	lk_unit_trace_wall_kernel<<<1, 1>>>(c, d_in, d_out, d_i);
+	lk_unit_trace_wall_kernel<<<1, 32>>>(c, d_in, d_out, d_i);
 	LCK(cudaGetLastError());
 	int hi[3];
 	LCK(cudaMemcpy(hi, d_i, 12, cudaMemcpyDeviceToHost));

@@ -23,7 +23,7 @@ const char *pcb_leak_last_error(void);
  * kind (0 ext, 1 int), coords(3), direction(3), elecv(3), n_refl, weights(nE). */
 int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src, uint64_t seed, int64_t id0, int64_t n, const double *coords, const double *dir,
 		 const double *ev, int8_t *status, int *irefl, double *fields, double *weights, int *leak_n, double **leak_rec, int64_t *n_leak_rec,
-		 int64_t *work /* [2] or NULL: capil_reflect events, wall-march steps (capil.c:1018-1068) */);
+		 int64_t *work /* [4] or NULL: capil_reflect events, wall-march steps (capil.c:1018-1068), steps actually evaluated, rounds of the segment scan */);
 
 /* One polycap_capil_reflect (mode 1) or polycap_capil_trace (mode 2) with leak_calc = true on one photon state:
  * in[16] = coords(3) direction(3) elecv(3) wall normal(3) i_refl d_travel A B (capillary axis: cap_x[i] = A*hexz[i], cap_y[i] = B*hexz[i]),
