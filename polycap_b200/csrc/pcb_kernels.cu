@@ -61,6 +61,7 @@ struct pcb_gpu_optic {
 	int nmax = 0, nE = 0;
 	PcbOptic o{};
 	double *d_tables = nullptr; /* z, cap, ext, hexz, rm: 5 x tb bytes */
+	double *d_leak_tables = nullptr; /* leak transport only: per z segment d ext/dz, d cap/dz, step length cap/10 and its reciprocal: 4 x tb bytes */
 	double *d_ec = nullptr;
 	double *d_wscratch = nullptr;
 	double *d_hist = nullptr; /* deferred weights: reflection history of the pool slots */
@@ -233,6 +234,23 @@ extern "C" pcb_gpu_optic *pcb_gpu_optic_create(int device, const pcb_optic_desc 
 		ok = cudaMemcpy(g->d_tables, g->h_tables, 5 * tb, cudaMemcpyHostToDevice) == cudaSuccess &&
 		     cudaMemcpy(g->d_ec, g->h_ec, g->ec_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
 	}
+	if (ok) { /* tables of the wall march (pcb_leak_core.cuh::LkCtx), host IEEE division = the bits the march's own expressions give */
+		std::vector<double> lt(4 * tn, 0.0);
+		double *lse = lt.data(), *lsc = lse + tn, *lsl = lsc + tn, *lis = lsl + tn;
+		for (int i = 0; i < n; i++) {
+			if (i + 1 < n) {
+				lse[i] = (d->ext[i + 1] - d->ext[i]) / (d->z[i + 1] - d->z[i]);
+				lsc[i] = (d->cap[i + 1] - d->cap[i]) / (d->z[i + 1] - d->z[i]);
+			}
+			lsl[i] = d->cap[i] / 10.;
+			lis[i] = 1.0 / lsl[i];
+		}
+		for (size_t i = n; i < tn; i++) {
+			lsl[i] = lsl[n - 1];
+			lis[i] = lis[n - 1];
+		}
+		ok = cudaMalloc(&g->d_leak_tables, 4 * tb) == cudaSuccess && cudaMemcpy(g->d_leak_tables, lt.data(), 4 * tb, cudaMemcpyHostToDevice) == cudaSuccess;
+	}
 	if (!ok) {
 		g_last_error = std::string("device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError());
 		pcb_gpu_optic_destroy(g);
@@ -266,7 +284,7 @@ extern "C" void pcb_gpu_optic_destroy(pcb_gpu_optic *g)
 	if (!g)
 		return;
 	cudaSetDevice(g->device);
-	cudaFree(g->d_tables); cudaFree(g->d_ec); cudaFree(g->d_wscratch); cudaFree(g->d_hist); cudaFree(g->d_wc);
+	cudaFree(g->d_tables); cudaFree(g->d_leak_tables); cudaFree(g->d_ec); cudaFree(g->d_wscratch); cudaFree(g->d_hist); cudaFree(g->d_wc);
 	cudaFree(g->d_status); cudaFree(g->d_fields); cudaFree(g->d_irefl); cudaFree(g->d_weights);
 	cudaFree(g->d_rank); cudaFree(g->d_blocksum); cudaFree(g->d_cutinfo); cudaFree(g->d_partial); cudaFree(g->d_cpartial);
 	cudaFree(g->d_rin);
@@ -1118,6 +1136,8 @@ static void leak_view(const pcb_gpu_optic *g, pcb_leak_optic *v)
 	v->nmax = g->nmax; v->nE = g->nE; v->mono = g->o.mono; v->monotonic = g->monotonic; v->sm_count = g->sm_count; v->device = g->device;
 	v->n_shells = g->o.n_shells; v->sig_rough = g->o.sig_rough; v->cap0 = g->cap0; v->ext0 = g->ext0;
 	v->d_z = g->o.z; v->d_cap = g->o.cap; v->d_ext = g->o.ext; v->d_hexz = g->o.hexz; v->d_ec = g->o.ec;
+	const size_t tn = g->table_bytes / 8;
+	v->d_se = g->d_leak_tables; v->d_sc = g->d_leak_tables + tn; v->d_sl = g->d_leak_tables + 2 * tn; v->d_isl = g->d_leak_tables + 3 * tn;
 }
 
 extern "C" int pcb_gpu_replay_leak(pcb_gpu_optic *g, int64_t n, const double *coords, const double *dir, const double *ev, int *ret, double *out_state,

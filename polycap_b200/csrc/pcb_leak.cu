@@ -22,7 +22,9 @@
 #include "pcb_leak.h"
 #include "pcb_leak_core.cuh"
 
+#ifndef LK_THREADS
 #define LK_THREADS 128
+#endif
 #define LK_WARPS (LK_THREADS / 32)
 #ifndef LK_BLOCKS_PER_SM
 #define LK_BLOCKS_PER_SM 1 /* registers as the code needs them: capping them at 128 (4 blocks, 16 warps per SM) measured 2.6x slower per warp */
@@ -316,6 +318,7 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	P.c.n_shells = o->n_shells;
 	P.c.sig_rough = o->sig_rough;
 	P.c.z = o->d_z; P.c.cap = o->d_cap; P.c.ext = o->d_ext; P.c.hexz = o->d_hexz; P.c.ec = o->d_ec;
+	P.c.se = o->d_se; P.c.sc = o->d_sc; P.c.sl = o->d_sl; P.c.isl = o->d_isl;
 	if (src) {
 		P.s.d_source = src->d_source; P.s.src_x = src->src_x; P.s.src_y = src->src_y; P.s.src_sigx = src->src_sigx; P.s.src_sigy = src->src_sigy;
 		P.s.src_shiftx = src->src_shiftx; P.s.src_shifty = src->src_shifty; P.s.hor_pol = src->hor_pol;
@@ -330,17 +333,20 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	 * workspace from a pool, and the ids that found the pool empty are redone by a second launch with full capacities (few warps). */
 	const size_t stride = 11 + (size_t)nE;
 	auto per_warp_bytes = [&](int depth, int rcap) { return (size_t)depth * sizeof(LkFrame) + (size_t)(depth + 1) * nE * 8 + (size_t)rcap * stride * 8; };
-	const int depth1 = getenv("POLYCAP_B200_LEAK_DEPTH1") ? atoi(getenv("POLYCAP_B200_LEAK_DEPTH1")) : 96;
-	const int rcap1 = 4 * depth1;
+	int depth1 = getenv("POLYCAP_B200_LEAK_DEPTH1") ? atoi(getenv("POLYCAP_B200_LEAK_DEPTH1")) : 96;
+	int rcap1 = 4 * depth1;
 	size_t free_b = 0, total_b = 0;
 	LCK(cudaMemGetInfo(&free_b, &total_b));
 	size_t budget = free_b / 3;
-	if (budget > ((size_t)24 << 30))
-		budget = (size_t)24 << 30;
+	if (budget > ((size_t)48 << 30))
+		budget = (size_t)48 << 30;
 	int per_sm = 0; /* resident blocks per SM: the persistent warps of a launch are exactly the ones the device holds at once */
 	LCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcb_leak_kernel, LK_THREADS, 0));
 	if (per_sm < 1)
 		per_sm = 1;
+	if (const char *ps = getenv("POLYCAP_B200_LEAK_BLOCKS_PER_SM")) /* tuning aid: fewer resident blocks than fit */
+		if (atoi(ps) >= 1 && atoi(ps) < per_sm)
+			per_sm = atoi(ps);
 	auto blocks_for = [&](int64_t items, int depth, int rcap) {
 		int blocks = (int)((items + LK_WARPS - 1) / LK_WARPS);
 		int max_blocks = (int)(budget / (per_warp_bytes(depth, rcap) * LK_WARPS));
@@ -350,6 +356,19 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 			max_blocks = 1;
 		return blocks > max_blocks ? max_blocks : blocks;
 	};
+	/* with one workspace per WARP (a few thousand per device) full capacities for everyone usually fit the budget -- 13.6 GB at 400
+	 * energies -- and then no photon ever moves or is redone; the small-workspace scheme above remains for very long grids */
+	bool all_full = false;
+	if (!getenv("POLYCAP_B200_LEAK_DEPTH1")) {
+		int want = (int)((n + LK_WARPS - 1) / LK_WARPS);
+		if (want > o->sm_count * per_sm)
+			want = o->sm_count * per_sm;
+		if ((size_t)want * LK_WARPS * per_warp_bytes(LK_DEPTH, LK_REC_CAP) <= budget) {
+			all_full = true;
+			depth1 = LK_DEPTH;
+			rcap1 = LK_REC_CAP;
+		}
+	}
 	int blocks = blocks_for(n, depth1, rcap1);
 	size_t warps = (size_t)blocks * LK_WARPS;
 	double *d_rin = nullptr;
@@ -375,6 +394,8 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 		const unsigned long long nb_max = bm ? (unsigned long long)atoll(bm) : 4096ULL;
 		if (nb > nb_max)
 			nb = nb_max;
+		if (all_full)
+			nb = 0;
 		P.big_n = nb;
 		LCK(M.alloc(&P.big_next, 8));
 		LCK(cudaMemset(P.big_next, 0, 8));
@@ -515,6 +536,7 @@ extern "C" int pcb_leak_unit_step(const pcb_leak_optic *o, int mode, const doubl
 	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
 	c.no_jump = getenv("POLYCAP_B200_LEAK_NO_JUMP") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
+	c.se = o->d_se; c.sc = o->d_sc; c.sl = o->d_sl; c.isl = o->d_isl;
 	const size_t nE = (size_t)o->nE, stride = 11 + nE;
 	*leak_rec = nullptr;
 	*n_leak_rec = 0;
@@ -557,6 +579,7 @@ extern "C" int pcb_leak_unit_trace_wall(const pcb_leak_optic *o, const double in
 	c.no_fast_march = getenv("POLYCAP_B200_LEAK_FULL_MARCH") ? 1 : 0;
 	c.no_jump = getenv("POLYCAP_B200_LEAK_NO_JUMP") ? 1 : 0;
 	c.z = o->d_z; c.cap = o->d_cap; c.ext = o->d_ext; c.hexz = o->d_hexz; c.ec = o->d_ec;
+	c.se = o->d_se; c.sc = o->d_sc; c.sl = o->d_sl; c.isl = o->d_isl;
 	DevMem M;
 	double *d_in, *d_out;
 	int *d_i;

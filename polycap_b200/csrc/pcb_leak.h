@@ -13,6 +13,7 @@ typedef struct {
 	int nmax, nE, mono, monotonic, sm_count, device;
 	double n_shells, sig_rough, cap0, ext0;
 	const double *d_z, *d_cap, *d_ext, *d_hexz, *d_ec;
+	const double *d_se, *d_sc, *d_sl, *d_isl; /* wall-march tables per z segment: d ext/dz, d cap/dz, cap/10, 10/cap */
 } pcb_leak_optic;
 
 const char *pcb_leak_last_error(void);

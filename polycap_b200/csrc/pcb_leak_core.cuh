@@ -115,6 +115,9 @@ struct LkCtx {
 	int no_jump;       /* POLYCAP_B200_LEAK_NO_JUMP=1: uneventful steps are recognised one by one instead of jumped over (checking aid) */
 	double n_shells, sig_rough;
 	const double *z, *cap, *ext, *hexz; /* global */
+	/* per z segment i, computed once on the host with the expressions the march uses (IEEE division: the same bits):
+	 * se = (ext[i+1]-ext[i])/(z[i+1]-z[i]), sc = (cap[i+1]-cap[i])/(z[i+1]-z[i]), sl = cap[i]/10 (the step length), isl = 1/sl */
+	const double *se, *sc, *sl, *isl;
 	const double *ec;                   /* [EC_ROWS][nE] */
 };
 
@@ -426,11 +429,10 @@ LK_INL void lk_march_seg_load(const LkCtx &c, LkMarchSeg &g, int zi)
 		return;
 	g.zi = zi;
 	g.z0 = c.z[zi];
-	const double dz = c.z[zi + 1] - g.z0;
 	g.e0 = c.ext[zi];
 	g.c0 = c.cap[zi];
-	g.se = (c.ext[zi + 1] - g.e0) / dz;
-	g.sc = (c.cap[zi + 1] - g.c0) / dz;
+	g.se = c.se[zi];
+	g.sc = c.sc[zi];
 }
 
 /* the point at path length dist, z segment zi (seg loaded): strictly inside cell (Ai, Bi), outside its bore, before the exit face */
@@ -448,19 +450,19 @@ LK_INL bool lk_march_uneventful(const LkCtx &c, const LkMarchSeg &g, const V3 &e
 /* returns the number of steps jumped (0: none) and advances dist accordingly; z_id (= zs) stays what it is */
 LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int zs, double &dist)
 {
-	/* Divisions here are multiplications by pcb_rcp_near() (a refined reciprocal, within an ulp): every bound derived from them is
-	 * backed off by whole steps and the landing point is verified, so nothing below needs a correctly rounded quotient.  What has to
-	 * be exact -- inc, rnd, nd -- is sums, differences and a product of an integer with a multiple of the binade's ulp. */
+	/* Bounds are kept as fractions num/den (den > 0) and compared by cross-multiplication; the two quotients that are needed come from
+	 * pcb_rcp_near() (a refined reciprocal, within an ulp): every bound is backed off by a whole step and the landing point is verified,
+	 * so nothing below needs a correctly rounded quotient.  What has to be exact -- inc, rnd, nd -- is sums, differences and the product
+	 * of an integer with a multiple of the binade's ulp. */
 	if (!(ed.z > 0.) || !(dist > 0.))
 		return 0;
 	const double z0 = c.z[zs], z1 = c.z[zs + 1];
 	const double pz = ec.z + dist * ed.z;
 	if (!(z0 <= pz && pz < z1))
 		return 0;
-	const double cstep = c.cap[zs] / 10.;
-	const double inv_cstep = pcb_rcp_near(cstep);
-	double smax = (z1 - pz) * pcb_rcp_near(ed.z);
-	if (!(smax * inv_cstep >= 7.))
+	const double cstep = c.sl[zs], inv_cstep = c.isl[zs];
+	double num = z1 - pz, den = ed.z; /* smax = num / den: the end of the segment */
+	if (!(num * inv_cstep >= 7. * den))
 		return 0; /* the segment ends within a few steps */
 	/* the increment the reference's additions realise in this binade */
 	const unsigned long long db = pcb_bits(dist);
@@ -478,8 +480,7 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 	if (!(fabs(rnd) < 0.5 * ulp))
 		return 0;                        /* half-way case: the additions alternate between two increments */
 	/* the zone along the ray, s = path length beyond the current point */
-	const double inv_dz = pcb_rcp_near(z1 - z0);
-	const double se = (c.ext[zs + 1] - c.ext[zs]) * inv_dz, sc = (c.cap[zs + 1] - c.cap[zs]) * inv_dz;
+	const double se = c.se[zs], sc = c.sc[zs];
 	const double t = pz - z0;
 	const double hz = (se * t + c.ext[zs]) * inv_den, hb = se * ed.z * inv_den;
 	const double rr = (sc * t + c.cap[zs]) * (1. + 1.e-9), rb = sc * ed.z * (1. + 1.e-9);
@@ -489,20 +490,28 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 	const double qc = ux * ux + uy * uy - rr * rr;
 	if (!(rr > 0. && hz > 0. && qc > 0.))
 		return 0;
-	{ /* three pairs of edge planes: |g + g1 s| < h + h1 s */
-		const double gx[3] = {1.0, 0.5, 0.5}, gy[3] = {0.0, PCB_COSPI_6, -PCB_COSPI_6};
-#pragma unroll 1
-		for (int k = 0; k < 3; k++) {
-			const double g = gx[k] * ux + gy[k] * uy, g1 = gx[k] * ux1 + gy[k] * uy1;
-			if (!(fabs(g) < h))
-				return 0;
-			/* g + g1 s = h + h1 s at s = (h - g)/(g1 - h1) if that is positive;  -(g + g1 s) = h + h1 s at s = (h + g)/(-g1 - h1) */
-			const double dp = g1 - h1, dm = -g1 - h1;
-			if (dp > 0. && (h - g) < smax * dp)
-				smax = (h - g) * pcb_rcp_near(dp);
-			if (dm > 0. && (h + g) < smax * dm)
-				smax = (h + g) * pcb_rcp_near(dm);
-		}
+	{ /* three pairs of edge planes |g + g1 s| < h + h1 s: g + g1 s reaches h + h1 s at (h - g)/(g1 - h1), -(g + g1 s) at (h + g)/(-g1 - h1) */
+		const double g0 = ux, g0s = ux1;
+		const double ga = 0.5 * ux + PCB_COSPI_6 * uy, gas = 0.5 * ux1 + PCB_COSPI_6 * uy1;
+		const double gb = 0.5 * ux - PCB_COSPI_6 * uy, gbs = 0.5 * ux1 - PCB_COSPI_6 * uy1;
+		if (!(fabs(g0) < h && fabs(ga) < h && fabs(gb) < h))
+			return 0;
+#define LK_EDGE(g, gs)                                              \
+	{                                                           \
+		const double dp = (gs)-h1, dm = -(gs)-h1;           \
+		if (dp > 0. && (h - (g)) * den < num * dp) {        \
+			num = h - (g);                              \
+			den = dp;                                   \
+		}                                                   \
+		if (dm > 0. && (h + (g)) * den < num * dm) {        \
+			num = h + (g);                              \
+			den = dm;                                   \
+		}                                                   \
+	}
+		LK_EDGE(g0, g0s)
+		LK_EDGE(ga, gas)
+		LK_EDGE(gb, gbs)
+#undef LK_EDGE
 	}
 	{ /* bore: qa s^2 + qb s + qc > 0, qc > 0: the smallest positive root, if any */
 		const double qa = ux1 * ux1 + uy1 * uy1 - rb * rb, qb = 2. * (ux * ux1 + uy * uy1 - rr * rb);
@@ -511,15 +520,21 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 			disc = 0.; /* a graze within rounding of a double root counts as one */
 		if (disc >= 0. && (qb < 0. || qa < 0.)) {
 			const double sq = sqrt(disc);
-			double root;
-			if (qb < 0.)
-				root = qc * pcb_rcp_near(-0.5 * (qb - sq));
-			else
-				root = -0.5 * (qb + sq) * pcb_rcp_near(qa);
-			if (root >= 0. && root < smax)
-				smax = root;
+			double rn, rd; /* root = rn / rd, rd > 0 */
+			if (qb < 0.) {
+				rn = qc;
+				rd = -0.5 * (qb - sq);
+			} else {
+				rn = 0.5 * (qb + sq);
+				rd = -qa;
+			}
+			if (rd > 0. && rn >= 0. && rn * den < num * rd) {
+				num = rn;
+				den = rd;
+			}
 		}
 	}
+	const double smax = num * pcb_rcp_near(den);
 	if (!(smax > 0.) || !(smax < 1.e30))
 		return 0;
 	double nf = floor(smax * inv_cstep * (1. - 1.e-7)) - 1.; /* at least one whole step short of the computed boundary (its rounding error is ~1e-12 of a step) */
@@ -537,7 +552,8 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 	if (!(z0 <= lz && lz < z1))
 		return 0;
 	LkMarchSeg g;
-	lk_march_seg_load(c, (g.zi = -1, g), zs);
+	g.zi = -1;
+	lk_march_seg_load(c, g, zs);
 	if (!lk_march_uneventful(c, g, ec, ed, Ai, Bi, inv_den, nd, lz))
 		return 0;
 	dist = nd;
@@ -593,8 +609,6 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 			const double Ai = (2. * q_i + r_i) * PCB_COSPI_6, Bi = r_i * (3. / 2);
 			LkMarchSeg sg;
 			sg.zi = -1;
-			int step_z = -1;
-			double step_len = 0;
 			int wait = 0; /* steps before the next attempt to jump (an attempt that found nothing to jump over is not repeated at once) */
 			for (;;) {
 				if (jump_ok) {
@@ -611,11 +625,7 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 				}
 				wk.wall_steps++;
 				wk.wall_evals++;
-				if (z_id != step_z) { /* one division per segment instead of one per step */
-					step_z = z_id;
-					step_len = c.cap[z_id] / 10.;
-				}
-				dist += step_len;
+				dist += c.sl[z_id]; /* cap[z_id] / 10. */
 				if (fast_ok) {
 					const double p0z = ec.z + dist * ed.z;
 					int zi = z_id;

@@ -30,6 +30,16 @@ long hl_replay(int nmax, const double *z, const double *cap, const double *ext, 
 	std::vector<double> zz(z, z + np), cc(cap, cap + np), ee(ext, ext + np);
 	zz.push_back(zz.back()); cc.push_back(cc.back()); ee.push_back(ee.back()); // the reference can read index nmax+1
 	LkCtx c{};
+	std::vector<double> se(np + 1, 0.), sc(np + 1, 0.), sl(np + 1, 0.), isl(np + 1, 0.);
+	for (int i = 0; i <= np; i++) {
+		if (i + 1 < np) {
+			se[i] = (ee[i + 1] - ee[i]) / (zz[i + 1] - zz[i]);
+			sc[i] = (cc[i + 1] - cc[i]) / (zz[i + 1] - zz[i]);
+		}
+		sl[i] = cc[i] / 10.;
+		isl[i] = 1.0 / sl[i];
+	}
+	c.se = se.data(); c.sc = sc.data(); c.sl = sl.data(); c.isl = isl.data();
 	c.nmax = nmax; c.nE = nE; c.mono = (n_shells == 0.); c.monotonic = 1;
 	for (int i = 0; i + 1 < np; i++)
 		if (!(z[i + 1] > z[i]))
@@ -83,6 +93,16 @@ int hl_trace_wall(int nmax, const double *z, const double *cap, const double *ex
 	for (int i = 0; i <= np; i++)
 		hexz[i] = ee[i] / (2. * PCB_COSPI_6 * (n_shells + 1));
 	LkCtx c{};
+	std::vector<double> se(np + 1, 0.), sc(np + 1, 0.), sl(np + 1, 0.), isl(np + 1, 0.);
+	for (int i = 0; i <= np; i++) {
+		if (i + 1 < np) {
+			se[i] = (ee[i + 1] - ee[i]) / (zz[i + 1] - zz[i]);
+			sc[i] = (cc[i + 1] - cc[i]) / (zz[i + 1] - zz[i]);
+		}
+		sl[i] = cc[i] / 10.;
+		isl[i] = 1.0 / sl[i];
+	}
+	c.se = se.data(); c.sc = sc.data(); c.sl = sl.data(); c.isl = isl.data();
 	c.nmax = nmax; c.nE = 0; c.mono = (n_shells == 0.); c.monotonic = 1;
 	c.no_fast_march = flags & 1;
 	c.no_jump = (flags >> 1) & 1;
