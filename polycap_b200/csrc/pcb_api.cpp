@@ -819,7 +819,18 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		pcb_gpu_memset(r.dev, r.d_sum, 0, nE * 8, leak_calc ? NULL : st);
 		pcb_gpu_memset(r.dev, r.d_cnt, 0, PCB_C_COUNT * 8, leak_calc ? NULL : st);
 	}
-	std::vector<double> leak_all; /* concatenated leak records of counted photons */
+	/* leak records of counted photons, wave by wave (the malloc'd blocks the waves return, not copied) */
+	struct LeakChunk {
+		double *rec;
+		int64_t n;
+	};
+	struct LeakChunks : std::vector<LeakChunk> {
+		~LeakChunks()
+		{
+			for (LeakChunk &c : *this)
+				free(c.rec);
+		}
+	} leak_chunks;
 	int64_t n_leak_all = 0;
 
 	/* the host block whose slices are the arrays of struct _polycap_images: the devices copy their records straight into it,
@@ -906,8 +917,9 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 				continue;
 			}
 			if (rc == 0 && n_lrec > 0) {
-				leak_all.insert(leak_all.end(), lrec, lrec + (size_t)n_lrec * (11 + nE));
+				leak_chunks.push_back(LeakChunk{lrec, n_lrec});
 				n_leak_all += n_lrec;
+				lrec = NULL;
 			}
 			free(lrec);
 			if (rc)
@@ -989,8 +1001,9 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 	if (leak_calc) {
 		const size_t stride = 11 + nE;
 		int64_t n_ext = 0, n_int = 0;
-		for (int64_t i = 0; i < n_leak_all; i++)
-			(leak_all[(size_t)i * stride] == 0. ? n_ext : n_int)++;
+		for (const LeakChunk &ch : leak_chunks)
+			for (int64_t i = 0; i < ch.n; i++)
+				(ch.rec[(size_t)i * stride] == 0. ? n_ext : n_int)++;
 		im->i_extleak = n_ext;
 		im->i_intleak = n_int;
 		auto alloc_d = [](int64_t n) { return (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1)); };
@@ -1008,8 +1021,9 @@ extern "C" polycap_transmission_efficiencies *polycap_source_get_transmission_ef
 		im->extleak_n_refl = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_ext > 0 ? n_ext : 1));
 		im->intleak_n_refl = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_int > 0 ? n_int : 1));
 		int64_t ie = 0, ii = 0;
-		for (int64_t i = 0; i < n_leak_all; i++) {
-			const double *r = leak_all.data() + (size_t)i * stride;
+		for (const LeakChunk &ch : leak_chunks)
+		for (int64_t i = 0; i < ch.n; i++) {
+			const double *r = ch.rec + (size_t)i * stride;
 			if (r[0] == 0.) {
 				for (int k = 0; k < 3; k++)
 					im->extleak_coords[k][ie] = r[1 + k];

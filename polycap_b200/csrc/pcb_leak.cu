@@ -265,6 +265,22 @@ __global__ void lk_unit_step_kernel(LkCtx c, int mode, const double *in, int ix,
 	}
 }
 
+/* leak records of a wave from pool (arrival) order into id order: record k of id i goes to ordered[dst[i] + k] */
+__global__ void lk_gather_kernel(const double *pool, const unsigned long long *src, const unsigned long long *dst, const int *leak_n, unsigned long long stride,
+				 unsigned long long n, double *ordered)
+{
+	for (unsigned long long i = blockIdx.x; i < n; i += gridDim.x) {
+		const int m = leak_n[i];
+		if (m <= 0)
+			continue;
+		const double *from = pool + src[i] * stride;
+		double *to = ordered + dst[i] * stride;
+		const unsigned long long words = (unsigned long long)m * stride;
+		for (unsigned long long k = threadIdx.x; k < words; k += blockDim.x)
+			to[k] = from[k];
+	}
+}
+
 /* ------------------------------------------------------------------ host side */
 
 static thread_local std::string g_lk_err;
@@ -510,19 +526,28 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	LCK(cudaMemcpy(fields, P.fields, (size_t)n * nfields * 8, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(weights, P.weights, (size_t)n * nE * 8, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(leak_n, P.leak_n, (size_t)n * 4, cudaMemcpyDeviceToHost));
-	/* records: pool order is arrival order; return them in id order */
-	std::vector<unsigned long long> off((size_t)n);
-	LCK(cudaMemcpy(off.data(), P.leak_off, (size_t)n * 8, cudaMemcpyDeviceToHost));
-	std::vector<double> pool((size_t)used * stride);
-	if (used)
-		LCK(cudaMemcpy(pool.data(), P.leak_pool, pool.size() * 8, cudaMemcpyDeviceToHost));
-	double *recs = (double *)malloc((used ? (size_t)used : 1) * stride * 8);
+	/* records: pool order is arrival order; they are put in id order on the device (lk_gather_kernel) and come back in one copy */
+	std::vector<unsigned long long> dst((size_t)n);
 	size_t w = 0;
-	for (int64_t i = 0; i < n; i++)
-		if (leak_n[i] > 0) {
-			memcpy(recs + w * stride, pool.data() + (size_t)off[(size_t)i] * stride, (size_t)leak_n[i] * stride * 8);
-			w += (size_t)leak_n[i];
-		}
+	for (int64_t i = 0; i < n; i++) {
+		dst[(size_t)i] = (unsigned long long)w;
+		w += (size_t)(leak_n[i] > 0 ? leak_n[i] : 0);
+	}
+	double *recs = (double *)malloc((w ? w : 1) * stride * 8);
+	if (!recs) {
+		g_lk_err = "leak transport: out of host memory for the leak records";
+		return -1;
+	}
+	if (w) {
+		unsigned long long *d_dst = nullptr;
+		double *d_ordered = nullptr;
+		LCK(M.alloc(&d_dst, (size_t)n * 8));
+		LCK(M.alloc(&d_ordered, w * stride * 8));
+		LCK(cudaMemcpy(d_dst, dst.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+		lk_gather_kernel<<<o->sm_count * 8, 256>>>(P.leak_pool, P.leak_off, d_dst, P.leak_n, (unsigned long long)stride, (unsigned long long)n, d_ordered);
+		LCK(cudaGetLastError());
+		LCK(cudaMemcpy(recs, d_ordered, w * stride * 8, cudaMemcpyDeviceToHost));
+	}
 	*leak_rec = recs;
 	*n_leak_rec = (int64_t)w;
 	return 0;
