@@ -316,6 +316,21 @@ def measure_device(ctx, pc, src, nE, ids_per_step, steps, warmup, clocks=False, 
                 launches=int(k1[0] - k0[0]) + (2 if ctx.world > 1 else 0), clocks=clk, allreduce_ms=step_ms[steps])
 
 
+def leak_counts(te):
+    """i_extleak, i_intleak of the result's struct _polycap_images (src/polycap-private.h:156-181) -- read in place: the getters would
+    build one object per leak record (millions at 400 energies)"""
+    import ctypes as C
+    P = C.c_void_p
+
+    class _Im(C.Structure):
+        _fields_ = [("i_start", C.c_int64), ("i_exit", C.c_int64), ("arrays", P * 18), ("i_extleak", C.c_int64), ("ext", P * 7), ("i_intleak", C.c_int64)]
+
+    class _Te(C.Structure):
+        _fields_ = [("n_energies", C.c_size_t), ("energies", P), ("efficiencies", P), ("images", C.POINTER(_Im))]
+    im = C.cast(te._trans_eff, C.POINTER(_Te)).contents.images.contents
+    return int(im.i_extleak), int(im.i_intleak)
+
+
 def result_counts(te):
     import ctypes as C
 
@@ -458,14 +473,14 @@ def leak_record(ctx, pc, w, n_exit, cpu_seconds):
         te = src.get_transmission_efficiencies(-1, n_exit, True)
         dt = time.perf_counter() - t0
     started, exits = result_counts(te)
-    n_ext, n_int = sum(1 for _ in te.extleak_data), sum(1 for _ in te.intleak_data)
+    n_ext, n_int = leak_counts(te)
     cnt = pc.last_run_counters() or {}
     # SURVEY 8d flop model with the leak terms: 76 instead of 70 per (reflection x energy), 60 per step of the wall march
     flops = (F_LAUNCH * cnt.get("launched", 0) + F_REFL * cnt.get("refl_all", 0) + 76 * nE * cnt.get("refl_all", 0) + F_EXIT * exits + 60 * cnt.get("wall_steps", 0))
     out = {"workload": w["desc"] + " -- leak_calc = true", "n_energies": nE, "value": started / dt, "unit": "photons/s", "seconds": dt, "exits": exits,
            "simulated_photons": started, "external_leak_records": n_ext, "internal_leak_records": n_int,
            "reflection_events_incl_secondaries": cnt.get("refl_all"), "wall_march_steps": cnt.get("wall_steps"),
-           "wall_march_steps_evaluated": cnt.get("q_hit_batches"),
+           "wall_march_steps_evaluated": cnt.get("q_hit_batches"), "started_photons_per_s": started / dt, "exit_photons_per_s": exits / dt,
            "roofline": {"bound": "fp64", "achieved": flops / dt / 1e12, "peak": ctx.dfma_peak, "unit": "TFLOP/s", "frac": flops / dt / 1e12 / ctx.dfma_peak if ctx.dfma_peak else None,
                         "model": "155*launched + 445*refl + 76*nE*refl + 100*exit + 60*wall_steps (SURVEY 8d, leak terms; wall_steps = the steps of the reference's march, of which only wall_march_steps_evaluated are walked, the rest is jumped over exactly); segment steps of the leak tracer are not counted",
                         "kernel": "pcb_leak_kernel (one warp per primary photon: energies and segment scan dealt over the lanes, wall march jumped; explicit frame stack)"}}
@@ -656,6 +671,12 @@ def main():
                 line["leak_run"] = leak_record(ctx, pc, w, args.leaks, args.cpu_seconds)
             except Exception as exc:
                 line["leak_run"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        elif subs and world == 1:
+            # BASELINE configs[2] as it is written -- ellipsoidal optic, 400 energies, leak / recap transport ON -- inside the default line
+            try:
+                line["sub_records"]["ellip_leaks_on"] = leak_record(ctx, pc, WORKLOADS["ellip"], 20000, min(args.cpu_seconds, 10.0))
+            except Exception as exc:
+                line["sub_records"]["ellip_leaks_on"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 b = reference_sample(w, args.cpu_seconds)

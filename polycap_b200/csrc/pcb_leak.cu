@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(
 		total.wall_steps += wk.wall_steps;
 		total.wall_evals += wk.wall_evals;
 		total.scan_rounds += wk.scan_rounds;
+		total.scan_solves += wk.scan_solves;
 #ifdef LK_PROFILE
 		total.t_total += wk.t_total; total.t_wall += wk.t_wall; total.t_jump += wk.t_jump; total.t_scan += wk.t_scan; total.t_energy += wk.t_energy;
 		total.n_jump_try += wk.n_jump_try;
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(
 		atomicAdd(P.refl_events + 1, total.wall_steps);
 		atomicAdd(P.refl_events + 2, total.wall_evals);
 		atomicAdd(P.refl_events + 3, total.scan_rounds);
+		atomicAdd(P.refl_events + 10, total.scan_solves);
 #ifdef LK_PROFILE
 		atomicAdd(P.refl_events + 4, total.t_total);
 		atomicAdd(P.refl_events + 5, total.t_wall);
@@ -500,8 +502,8 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	LCK(cudaMemcpy(&used, P.leak_pool_used, 8, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(refl, P.refl_events, 128, cudaMemcpyDeviceToHost));
 	if (getenv("POLYCAP_B200_PHASES")) {
-		fprintf(stderr, "polycap-b200 phases: leak kernel %.1f ms (+ %.1f ms second launch): %llu reflection events, %llu march steps (%llu evaluated), %llu scan rounds\n",
-			kernel_ms, kernel2_ms, refl[0], refl[1], refl[2], refl[3]);
+		fprintf(stderr, "polycap-b200 phases: leak kernel %.1f ms (+ %.1f ms second launch): %llu reflection events, %llu march steps (%llu evaluated), %llu scan rounds, %llu solves in the scans for the next bore\n",
+			kernel_ms, kernel2_ms, refl[0], refl[1], refl[2], refl[3], refl[10]);
 #ifdef LK_PROFILE
 		const double tt = (double)refl[4] > 0 ? (double)refl[4] : 1.0;
 		fprintf(stderr, "polycap-b200 phases: leak clocks per reflection event (warp-time): total %.0f = wall march %.0f (of which jumps %.0f, %.2f attempts) + segment scan %.0f + energy loop %.0f + rest %.0f\n",

@@ -155,7 +155,8 @@ struct LkWork {
 	unsigned long long refl_events; /* capil_reflect calls incl. secondaries */
 	unsigned long long wall_steps;  /* steps of the reference's wall march this photon stands for (capil.c:1018-1068) */
 	unsigned long long wall_evals;  /* steps actually evaluated (the rest was jumped over) */
-	unsigned long long scan_rounds; /* rounds of the lane-parallel segment scan */
+	unsigned long long scan_rounds; /* rounds of the lane-parallel segment scans */
+	unsigned long long scan_solves; /* full solves of the scan for the next bore (per lane; the other segments were ruled out from the quadratic's coefficients) */
 #ifdef LK_PROFILE
 	unsigned long long t_total, t_wall, t_jump, t_scan, t_energy, n_jump_try; /* SM clocks per phase (tuning builds: -DLK_PROFILE) */
 #endif
@@ -448,8 +449,11 @@ LK_INL bool lk_march_uneventful(const LkCtx &c, const LkMarchSeg &g, const V3 &e
 }
 
 /* returns the number of steps jumped (0: none) and advances dist accordingly; z_id (= zs) stays what it is */
-LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int zs, double &dist)
+/* the jump within z segment zs and within the binade of dist; seg_end: the end of the segment or of the binade, not an event, is what
+ * stopped it (the next step or two cross it) */
+LK_INL unsigned long long lk_jump_in_segment(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int zs, double &dist, bool &seg_end)
 {
+	seg_end = false;
 	/* Bounds are kept as fractions num/den (den > 0) and compared by cross-multiplication; the two quotients that are needed come from
 	 * pcb_rcp_near() (a refined reciprocal, within an ulp): every bound is backed off by a whole step and the landing point is verified,
 	 * so nothing below needs a correctly rounded quotient.  What has to be exact -- inc, rnd, nd -- is sums, differences and the product
@@ -462,8 +466,7 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 		return 0;
 	const double cstep = c.sl[zs], inv_cstep = c.isl[zs];
 	double num = z1 - pz, den = ed.z; /* smax = num / den: the end of the segment */
-	if (!(num * inv_cstep >= 7. * den))
-		return 0; /* the segment ends within a few steps */
+	bool at_seg_end = true;
 	/* the increment the reference's additions realise in this binade */
 	const unsigned long long db = pcb_bits(dist);
 	const int ex = (int)((db >> 52) & 0x7ffULL);
@@ -502,10 +505,12 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 		if (dp > 0. && (h - (g)) * den < num * dp) {        \
 			num = h - (g);                              \
 			den = dp;                                   \
+			at_seg_end = false;                         \
 		}                                                   \
 		if (dm > 0. && (h + (g)) * den < num * dm) {        \
 			num = h + (g);                              \
 			den = dm;                                   \
+			at_seg_end = false;                         \
 		}                                                   \
 	}
 		LK_EDGE(g0, g0s)
@@ -531,33 +536,95 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 			if (rd > 0. && rn >= 0. && rn * den < num * rd) {
 				num = rn;
 				den = rd;
+				at_seg_end = false;
 			}
 		}
 	}
 	const double smax = num * pcb_rcp_near(den);
 	if (!(smax > 0.) || !(smax < 1.e30))
 		return 0;
-	double nf = floor(smax * inv_cstep * (1. - 1.e-7)) - 1.; /* at least one whole step short of the computed boundary (its rounding error is ~1e-12 of a step) */
+	/* Steps that stay inside: one whole step short of an event (the rounding error of the bound is ~1e-12 of a step); when it is the
+	 * end of the segment that bounds them, right up to it -- the landing point is checked against z1 with the march's own expression,
+	 * and one step is given back if it fails. */
+	double nf = floor(smax * inv_cstep * (1. - 1.e-7)) - (at_seg_end ? 0. : 1.);
 	{ /* stay inside the binade */
 		const double nb = floor((top - dist) * pcb_rcp_near(inc) * (1. - 1.e-7)) - 1.;
-		nf = nb < nf ? nb : nf;
+		if (nb < nf) { /* the end of the binade bounds the run: like the end of a segment, the next step or two cross it */
+			nf = nb;
+			at_seg_end = true;
+		}
 	}
-	if (!(nf >= 4.) || nf > 4.e15)
-		return 0;
-	const double nd = dist + nf * inc;       /* exact */
-	if (!(nd < top))
-		return 0;
-	/* the landing point: same segment, inside the zone */
-	const double lz = ec.z + nd * ed.z;
-	if (!(z0 <= lz && lz < z1))
-		return 0;
 	LkMarchSeg g;
 	g.zi = -1;
 	lk_march_seg_load(c, g, zs);
-	if (!lk_march_uneventful(c, g, ec, ed, Ai, Bi, inv_den, nd, lz))
-		return 0;
-	dist = nd;
-	return (unsigned long long)nf;
+#pragma unroll 1
+	for (int attempt = 0; attempt < 2; attempt++, nf -= 1.) {
+		if (!(nf >= 1.) || nf > 4.e15)
+			return 0;
+		const double nd = dist + nf * inc;       /* exact */
+		if (!(nd < top))
+			continue;
+		/* the landing point: same segment, inside the zone */
+		const double lz = ec.z + nd * ed.z;
+		if (!(z0 <= lz && lz < z1))
+			continue;
+		if (!lk_march_uneventful(c, g, ec, ed, Ai, Bi, inv_den, nd, lz))
+			return 0;
+		dist = nd;
+		seg_end = at_seg_end;
+		return (unsigned long long)nf;
+	}
+	return 0;
+}
+
+/* The march from (dist, z_id) on for as long as nothing happens, segment after segment: jump to the end of the segment, take the step
+ * or two that cross into the next one -- each the reference's own addition dist + cap[z_id]/10, accepted only if its point is
+ * uneventful -- and jump again; the end of the binade of dist (where the increment the additions realise changes) is crossed the
+ * same way.  Returns the number of the reference's steps this stands for; on return (dist, z_id) is the state
+ * after the last of them, and the caller's next ordinary step sees whatever stopped the run. */
+LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int &z_id, double &dist, unsigned long long &n_eval)
+{
+	const int nm = c.nmax;
+	unsigned long long total = 0;
+	int zs = z_id;
+	LkMarchSeg g;
+	g.zi = -1;
+#pragma unroll 1
+	for (;;) {
+		bool seg_end = false;
+		const unsigned long long nj = lk_jump_in_segment(c, ec, ed, Ai, Bi, inv_den, zs, dist, seg_end);
+		total += nj;
+		if (nj == 0 && total == 0)
+			break; /* nothing to jump over where the march stands: the caller walks */
+		if (nj != 0 && !seg_end)
+			break; /* an event (or the end of the binade) is near: the caller's ordinary steps take over */
+		/* cross into the next segment / the next binade: at most three single steps */
+		bool crossed = false;
+		const unsigned ex0 = pcb_hi_word(dist) >> 20;
+#pragma unroll 1
+		for (int k = 0; k < 3 && !crossed; k++) {
+			const double d2 = dist + c.sl[zs];
+			const double p2z = ec.z + d2 * ed.z;
+			int zi = zs;
+			while (zi + 1 < nm && c.z[zi + 1] <= p2z)
+				zi++;
+			lk_march_seg_load(c, g, zi);
+			n_eval++;
+			if (!lk_march_uneventful(c, g, ec, ed, Ai, Bi, inv_den, d2, p2z)) {
+				n_eval--; /* not taken: the caller's ordinary step evaluates (and counts) it */
+				z_id = zs;
+				return total;
+			}
+			dist = d2;
+			total++;
+			crossed = zi != zs || (pcb_hi_word(d2) >> 20) != ex0;
+			zs = zi;
+		}
+		if (!crossed)
+			break;
+	}
+	z_id = zs;
+	return total;
 }
 
 /* capil.c:896-1194; ed is normalised in place like the reference does with photon->exit_direction */
@@ -614,7 +681,7 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 				if (jump_ok) {
 					if (wait == 0) {
 						const unsigned long long tj = LK_CLOCK();
-						const unsigned long long nj = lk_march_jump(c, ec, ed, Ai, Bi, inv_den, z_id, dist);
+						const unsigned long long nj = lk_march_jump(c, ec, ed, Ai, Bi, inv_den, z_id, dist, wk.wall_evals);
 						LK_TIME(t_jump, tj);
 						LK_COUNT(n_jump_try);
 						wk.wall_steps += nj;
@@ -689,6 +756,14 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 				const double den = 2. * PCB_COSPI_6 * (n_shells + 1);
 				bool found = false;
 				int iesc_last = 0;
+				/* Most of these segments are nowhere near the bore.  The solve's own quadratic a d^2 + b d + c in d = z - z[i] (same
+				 * expressions, same bits: capil.c:105-124) tells without a root or a division more: no real root (the solve's own -2), or
+				 * both ends of the segment outside the cone by a margin with the parabola's vertex outside the segment -- then no root
+				 * lies within the segment and the solve cannot return 1 (capil.c:125-177); only the other segments are solved. */
+				V3 dn = ed;
+				norm3(dn);
+				const PcbDivisor dn_z = pcb_divisor(dn.z);
+				const double rx = pcb_div(dn.x, dn_z), ry = pcb_div(dn.y, dn_z);
 				for (int i0 = z_first; i0 <= z_last && !found; i0 += LK_LANES) {
 					wk.scan_rounds++;
 					const int i = i0 + lk_lane();
@@ -704,7 +779,29 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 						c1.y = Bq * hexz;
 						c1.x = Aq * hexz;
 						c1.z = c.z[i + 1];
-						mine = lk_segment_checked(c0, c1, c.cap[i], c.cap[i + 1], p0, ed, my_hit, my_sn);
+						const double r0 = c.cap[i], r1 = c.cap[i + 1];
+						bool solve = true;
+						if (!c.no_fast_march && !(c0.z < 0. || c1.z < 0 || r0 < 0. || r1 < 0. || ed.z < 0 || c1.z <= c0.z)) {
+							const double ax = c1.x - c0.x, ay = c1.y - c0.y, az = c1.z - c0.z;
+							const PcbDivisor az_d = pcb_divisor(az);
+							const double ux = rx - pcb_div(ax, az_d), uy = ry - pcb_div(ay, az_d);
+							const double sl = (r1 - r0) / (c1.z - c0.z);
+							const double qa = (ux * ux + uy * uy - sl * sl);
+							const double qb = (2. * (p0.x - c0.x) * ux + 2. * (p0.y - c0.y) * uy - 2. * r0 * sl);
+							const double qc = ((p0.x - c0.x) * (p0.x - c0.x) + (p0.y - c0.y) * (p0.y - c0.y) - r0 * r0);
+							if (qb * qb - 4. * qa * qc < 0) {
+								solve = false;
+							} else {
+								const double ql = (qa * az + qb) * az + qc, margin = 1.e-8 * r0 * r0;
+								if (qc > margin && ql > margin && (qa <= 0. || qb >= 0. || 2. * qa * az + qb <= 0.))
+									solve = false;
+							}
+						}
+						mine = -3;
+						if (solve) {
+							wk.scan_solves++;
+							mine = lk_segment_checked(c0, c1, r0, r1, p0, ed, my_hit, my_sn);
+						}
 					}
 					const unsigned hits = lk_ballot(i <= z_last && mine == 1);
 					if (hits) {

@@ -15,7 +15,7 @@ extern "C" {
 // replay n start states with leak_calc = true.
 // flags: bit 0 = full march everywhere (no uneventful-step shortcut), bit 1 = no jumps (uneventful steps one by one)
 // out_state [n][11]: exit coords, exit direction, electric vector, d_travel, i_refl; recs [rec_cap][12+nE]: photon, kind, coords(3), direction(3), elecv(3), n_refl, weights
-// work[4]: reflection events, wall-march steps (reference-equivalent), steps evaluated, scan rounds
+// work[5]: reflection events, wall-march steps (reference-equivalent), steps evaluated, scan rounds, full solves of the next-bore scan
 long hl_replay(int nmax, const double *z, const double *cap, const double *ext, double n_cap, double sig_rough, double density, int nE, const double *energies,
 	       const double *amu, const double *scatf, int flags, long n, const double *start /* [n][9] */, int *ret, double *out_state, double *weights,
 	       long *leak_n, double *recs, long rec_cap, unsigned long long *work)
@@ -51,7 +51,7 @@ long hl_replay(int nmax, const double *z, const double *cap, const double *ext, 
 	std::vector<LkFrame> frames(LK_DEPTH);
 	std::vector<double> arena((size_t)(LK_DEPTH + 1) * nE), strip((size_t)LK_REC_CAP * (11 + nE));
 	long nrec_total = 0;
-	LkWork total = {0, 0, 0, 0};
+	LkWork total{};
 	for (long i = 0; i < n; i++) {
 		const double *s = start + 9 * i;
 		V3 sc = {s[0], s[1], s[2]}, sd = {s[3], s[4], s[5]}, sev = {s[6], s[7], s[8]};
@@ -60,11 +60,11 @@ long hl_replay(int nmax, const double *z, const double *cap, const double *ext, 
 		LkFrame *fr = frames.data();
 		double *ar = arena.data();
 		LkResult r;
-		LkWork wk = {0, 0, 0, 0};
+		LkWork wk{};
 		lk_photon(c, sc, sd, sev, 0.0, fr, ar, out, r, wk);
 		if (out.err)
 			return -out.err;
-		total.refl_events += wk.refl_events; total.wall_steps += wk.wall_steps; total.wall_evals += wk.wall_evals; total.scan_rounds += wk.scan_rounds;
+		total.refl_events += wk.refl_events; total.wall_steps += wk.wall_steps; total.wall_evals += wk.wall_evals; total.scan_rounds += wk.scan_rounds; total.scan_solves += wk.scan_solves;
 		ret[i] = r.ret;
 		double *o = out_state + 11 * i;
 		o[0] = r.ec.x; o[1] = r.ec.y; o[2] = r.ec.z; o[3] = r.ed.x; o[4] = r.ed.y; o[5] = r.ed.z; o[6] = r.ev.x; o[7] = r.ev.y; o[8] = r.ev.z;
@@ -79,7 +79,7 @@ long hl_replay(int nmax, const double *z, const double *cap, const double *ext, 
 			memcpy(d + 1, strip.data() + (size_t)k * (11 + nE), (size_t)(11 + nE) * 8);
 		}
 	}
-	work[0] = total.refl_events; work[1] = total.wall_steps; work[2] = total.wall_evals; work[3] = total.scan_rounds;
+	work[0] = total.refl_events; work[1] = total.wall_steps; work[2] = total.wall_evals; work[3] = total.scan_rounds; work[4] = total.scan_solves;
 	return nrec_total;
 }
 
@@ -109,7 +109,7 @@ int hl_trace_wall(int nmax, const double *z, const double *cap, const double *ex
 	c.n_shells = n_shells;
 	c.z = zz.data(); c.cap = cc.data(); c.ext = ee.data(); c.hexz = hexz.data();
 	V3 ec = {in6[0], in6[1], in6[2]}, ed = {in6[3], in6[4], in6[5]};
-	LkWork wk = {0, 0, 0, 0};
+	LkWork wk{};
 	int rc = lk_trace_wall(c, ec, ed, *d_travel, rq[0], rq[1], wk);
 	work[0] = wk.wall_steps; work[1] = wk.wall_evals;
 	return rc;

@@ -52,7 +52,7 @@ def replay(L, g, start, flags=0, energies=None, amu=None, scatf=None):
     ln = np.zeros(n, dtype=np.int64)
     cap_rec = 200000
     recs = np.zeros((cap_rec, 12 + nE))
-    work = (C.c_ulonglong * 4)()
+    work = (C.c_ulonglong * 5)()
     k = L.hl_replay(int(g["nmax"]), _p(z), _p(cap), _p(ext), float(g["n_cap"]), float(g["sig_rough"]), float(g["density"]), nE, _p(energies), _p(amu),
                     _p(scatf), flags, n, _p(start), ret.ctypes.data_as(C.POINTER(C.c_int)), _p(state), _p(w), ln.ctypes.data_as(C.POINTER(C.c_long)),
                     _p(recs), cap_rec, work)
