@@ -138,3 +138,50 @@ def test_jump_on_long_grid_and_many_photons(hl):
     for k in ("ret", "state", "weights", "leak_n", "recs"):
         assert np.array_equal(jump[k], walk[k], equal_nan=True), k
     assert jump["work"][1] == walk["work"][1] and jump["recs"].shape[0] > 100
+
+
+@pytest.mark.parametrize("name,n", [("xos1", 120), ("dubfoc", 120), ("parab", 120), ("conical", 200)])
+def test_jump_on_other_geometries(hl, name, n):
+    """the measured XOS profile (non-uniform z table), the double-focusing optic with rough walls (the roughness term of the energy loop),
+    the paraboloidal and the conical profile with leaks on: the jumped march against the walked one, bit for bit"""
+    from conftest import load_golden
+    g = load_golden(name)
+    st = g["start"][:n]
+    jump = replay(hl, g, st)
+    walk = replay(hl, g, st, flags=2)
+    for k in ("ret", "state", "weights", "leak_n", "recs"):
+        assert np.array_equal(jump[k], walk[k], equal_nan=True), k
+    assert jump["work"][:2] == walk["work"][:2]
+    assert jump["work"][0] > 100  # reflections happened
+    full = replay(hl, g, st[:16], flags=1)
+    for k in ("ret", "state", "weights", "leak_n"):
+        assert np.array_equal(jump[k][:16], full[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("name", ["xos1", "dubfoc", "monocap"])
+def test_host_state_machine_matches_oracle_live_on_other_geometries(hl, harness, orc, name):
+    """a few photons of other geometries through the oracle (the C restatement of the reference, leaks on, full march) and through the
+    host build of the leak state machine: codes, reflection counts, leak counts exact, weights and leak records to 1e-9"""
+    from conftest import load_golden, optic_of
+    g = load_golden(name)
+    o = optic_of(harness, g)
+    n = 10
+    st = g["start"][:n]
+    mine = replay(hl, g, st)
+    nE = len(g["energies"])
+    k = 0
+    for i in range(n):
+        ph = orc.photon(o, st[i, 0:3], st[i, 3:6], st[i, 6:9])
+        r, w = orc.launch(o, ph, leak=True)
+        assert r == mine["ret"][i] and ph.i_refl == int(mine["state"][i, 10]), (i, r, mine["ret"][i])
+        lk = orc.leaks(ph, nE)
+        recs = mine["recs"][mine["recs"][:, 0] == i]
+        for kind, key in ((0, "ext"), (1, "int")):
+            got = recs[recs[:, 1] == kind]
+            assert len(got) == len(lk[key]), (i, key)
+            for a, b in zip(got, lk[key]):
+                k += 1
+                assert rel_err(a[2:5], b["coords"]) <= RTOL and rel_err(a[12:], b["weight"]) <= RTOL and int(a[11]) == b["n_refl"]
+        if r in (0, 1):
+            assert rel_err(mine["weights"][i], w) <= RTOL
+        orc.L.orc_photon_clear_leaks(C.byref(ph))
