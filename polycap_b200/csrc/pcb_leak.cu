@@ -20,6 +20,9 @@
 #include "pcb_device.cuh"
 #include "pcb_gpu.h"
 #include "pcb_leak.h"
+#if !defined(LK_UNPHASED) && !defined(LK_PHASED)
+#define LK_PHASED 1 /* the warps of a block take the phases of a reflection event in step (pcb_leak_core.cuh): 1.3x on the B200 */
+#endif
 #include "pcb_leak_core.cuh"
 
 #ifndef LK_THREADS
@@ -76,6 +79,9 @@ __global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(
 	LkOut out;
 	out.big_frames = P.big_frames; out.big_arena = P.big_arena; out.big_rec = P.big_rec; out.big_next = P.big_next; out.big_n = P.big_n;
 	LkWork total{};
+#ifdef LK_PHASED
+	int phase_clock = 0;
+#endif
 	for (;;) {
 		unsigned long long i = lk_fetch_add(P.next, 1ULL);
 		if (P.todo) {
@@ -104,8 +110,14 @@ __global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(
 		LkFrame *frames = frames0;
 		LkResult r;
 		LkWork wk{};
+#ifdef LK_PHASED
+		wk.phase.clock = phase_clock;
+#endif
 		lk_sync(); /* the previous photon's copy-out has read this workspace across lanes */
 		lk_photon(c, s0.coords, s0.dir, s0.ev, 0.0, frames, arena, out, r, wk);
+#ifdef LK_PHASED
+		phase_clock = wk.phase.clock;
+#endif
 		if (out.err) {
 			if (P.retry) { /* did not fit the small per-warp capacities: the second launch redoes this id with the full ones */
 				const unsigned long long slot = lk_fetch_add(P.n_retry, 1ULL);
@@ -196,6 +208,10 @@ __global__ void __launch_bounds__(LK_THREADS, LK_BLOCKS_PER_SM) pcb_leak_kernel(
 		if (lane == 0)
 			P.leak_n[i] = keep;
 	}
+#ifdef LK_PHASED
+	while (__syncthreads_or(0)) { /* out of photons: keep the block's clock ticking until its other warps are done too */
+	}
+#endif
 	if (lane == 0) {
 		atomicAdd(P.refl_events, total.refl_events);
 		atomicAdd(P.refl_events + 1, total.wall_steps);
