@@ -129,6 +129,10 @@ LK_INL void lk_phase_enter(LkPhase &ph, int want)
 #define LK_PHASE(want) ((void)0)
 #endif
 
+#ifndef LK_W_BUDGET
+#define LK_W_BUDGET 0 /* tuning variant, not used: segment / binade crossings of a wall march per tick of the block's clock (0: the whole march in one tick).  Marches average 8 segments and 10 % exceed 16, so the block waits for its longest march; taking marches in stretches of 5 / 8 / 12 crossings was measured 41 % / 25 % / 24 % SLOWER on the B200 (a warp that comes back for the next stretch sits out a whole turn of the clock) */
+#endif
+
 /* Capacities per primary photon.  A hard photon at a steep angle crosses capillary after capillary, each crossing one
  * nested secondary (the reference recurses just as deep: its corpus shows 440 leak records and i_refl 568 on one photon). */
 #define LK_DEPTH 1400    /* frames: primary + nested secondaries */
@@ -612,8 +616,10 @@ LK_INL unsigned long long lk_jump_in_segment(const LkCtx &c, const V3 &ec, const
  * uneventful -- and jump again; the end of the binade of dist (where the increment the additions realise changes) is crossed the
  * same way.  Returns the number of the reference's steps this stands for; on return (dist, z_id) is the state
  * after the last of them, and the caller's next ordinary step sees whatever stopped the run. */
-LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int &z_id, double &dist, unsigned long long &n_eval)
+LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &ed, double Ai, double Bi, double inv_den, int &z_id, double &dist, unsigned long long &n_eval,
+					 int max_cross, int &n_cross)
 {
+	n_cross = 0;
 	const int nm = c.nmax;
 	unsigned long long total = 0;
 	int zs = z_id;
@@ -652,6 +658,8 @@ LK_DEV unsigned long long lk_march_jump(const LkCtx &c, const V3 &ec, const V3 &
 		}
 		if (!crossed)
 			break;
+		if (++n_cross >= max_cross)
+			break; /* the caller's budget for one stretch (LK_W_BUDGET) */
 	}
 	z_id = zs;
 	return total;
@@ -706,16 +714,24 @@ LK_DEV int lk_trace_wall(const LkCtx &c, const V3 &ec, V3 &ed, double &d_travel,
 			const double Ai = (2. * q_i + r_i) * PCB_COSPI_6, Bi = r_i * (3. / 2);
 			LkMarchSeg sg;
 			sg.zi = -1;
+			int budget = 0;
 			int wait = 0; /* steps before the next attempt to jump (an attempt that found nothing to jump over is not repeated at once) */
 			for (;;) {
 				if (jump_ok) {
 					if (wait == 0) {
 						const unsigned long long tj = LK_CLOCK();
-						const unsigned long long nj = lk_march_jump(c, ec, ed, Ai, Bi, inv_den, z_id, dist, wk.wall_evals);
+						int crossed = 0;
+						const unsigned long long nj = lk_march_jump(c, ec, ed, Ai, Bi, inv_den, z_id, dist, wk.wall_evals, LK_W_BUDGET > 0 ? LK_W_BUDGET : 0x7fffffff, crossed);
+						if (LK_W_BUDGET > 0 && (budget += crossed) >= LK_W_BUDGET) {
+							/* a long march is taken in stretches of LK_W_BUDGET segment / binade crossings, one per tick of the block's clock, so that
+							 * the other warps of the block do not wait at the barrier for the longest of their marches (LK_PHASED; a no-op otherwise) */
+							budget = 0;
+							LK_PHASE(LK_PH_W);
+						}
 						LK_TIME(t_jump, tj);
 						LK_COUNT(n_jump_try);
 						wk.wall_steps += nj;
-						wait = nj ? 2 : 4; /* after a jump the next event or the end of the segment is one or two steps away */
+						wait = (LK_W_BUDGET > 0 && crossed >= LK_W_BUDGET) ? 0 : (nj ? 2 : 4); /* after a jump that ran its course the next event or the end of the segment is one or two steps away */
 					} else {
 						wait--;
 					}
