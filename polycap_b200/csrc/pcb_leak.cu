@@ -518,7 +518,7 @@ extern "C" int pcb_leak_run(const pcb_leak_optic *o, const pcb_source_desc *src,
 	LCK(cudaMemcpy(&used, P.leak_pool_used, 8, cudaMemcpyDeviceToHost));
 	LCK(cudaMemcpy(refl, P.refl_events, 128, cudaMemcpyDeviceToHost));
 	if (getenv("POLYCAP_B200_PHASES")) {
-		fprintf(stderr, "polycap-b200 phases: leak kernel %.1f ms (+ %.1f ms second launch): %llu reflection events, %llu march steps (%llu evaluated), %llu scan rounds, %llu solves in the scans for the next bore\n",
+		fprintf(stderr, "polycap-b200 phases: leak kernel %.1f ms (+ %.1f ms second launch): %llu reflection events, %llu march steps (%llu evaluated), %llu scan rounds, %llu solves by lane 0 in the scans for the next bore\n",
 			kernel_ms, kernel2_ms, refl[0], refl[1], refl[2], refl[3], refl[10]);
 #ifdef LK_PROFILE
 		const double tt = (double)refl[4] > 0 ? (double)refl[4] : 1.0;
